@@ -1,0 +1,148 @@
+// dynamics.cuh -- device dynamics models for the fused rollout kernel.
+//
+//  * NetChain<R, 6,32,32,4>: the NeuralNetModel MLP (PI/neural_net_model.cu:357-410) for R rollouts
+//    held in one thread's registers.  Weights are staged once per CTA in shared memory in a
+//    transposed layout Wt[k][j], so for a fixed input k the OUT weights are contiguous: one
+//    broadcast LDS.128 feeds 4*R FFMAs.  Per output neuron the products are accumulated for k
+//    ascending from 0 with FMA and the bias is added afterwards -- the reference's order.
+//  * CarBasisModel: GeneralizedLinear<CarBasisFuncs,7,2,25,CarKinematics,3>
+//    (PI/generalized_linear.cu:225-245, PI/car_bfs.cuh:44-120) as straight-line code with the shared
+//    sub-expressions (front slip tangent, rear slip ratio, sin(steer)) evaluated once.
+#pragma once
+#include "device_common.cuh"
+
+namespace mppi {
+
+// ---- packed transposed parameter layout ------------------------------------------------------
+// For widths w0..wL: for each layer l: Wt_l[w_l][w_{l+1}] (k-major) followed by b_l[w_{l+1}].
+template <int... W>
+struct NetShape;
+template <int A, int B2>
+struct NetShape<A, B2> {
+  static constexpr int NPARAMS = A * B2 + B2;
+  static constexpr int LAST = B2;
+  static constexpr int FIRST = A;
+};
+template <int A, int B2, int C, int... Rest>
+struct NetShape<A, B2, C, Rest...> {
+  static constexpr int NPARAMS = A * B2 + B2 + NetShape<B2, C, Rest...>::NPARAMS;
+  static constexpr int LAST = NetShape<B2, C, Rest...>::LAST;
+  static constexpr int FIRST = A;
+};
+
+template <int R, int IN, int OUT, bool ACT>
+__device__ __forceinline__ void dense_layer(const float *__restrict__ sw, const float (&a)[IN][R], float (&o)[OUT][R]) {
+  static_assert(OUT % 4 == 0, "layer width must be a multiple of 4");
+  const float4 *W4 = reinterpret_cast<const float4 *>(sw);
+#pragma unroll
+  for (int j = 0; j < OUT; j++)
+#pragma unroll
+    for (int r = 0; r < R; r++) o[j][r] = 0.0f;
+#pragma unroll
+  for (int k = 0; k < IN; k++) {
+#pragma unroll
+    for (int j4 = 0; j4 < OUT / 4; j4++) {
+      const float4 w = W4[k * (OUT / 4) + j4];
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        o[4 * j4 + 0][r] = fmaf(w.x, a[k][r], o[4 * j4 + 0][r]);
+        o[4 * j4 + 1][r] = fmaf(w.y, a[k][r], o[4 * j4 + 1][r]);
+        o[4 * j4 + 2][r] = fmaf(w.z, a[k][r], o[4 * j4 + 2][r]);
+        o[4 * j4 + 3][r] = fmaf(w.w, a[k][r], o[4 * j4 + 3][r]);
+      }
+    }
+  }
+  const float4 *B4 = reinterpret_cast<const float4 *>(sw + IN * OUT);
+#pragma unroll
+  for (int j4 = 0; j4 < OUT / 4; j4++) {
+    const float4 b = B4[j4];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      float v0 = o[4 * j4 + 0][r] + b.x, v1 = o[4 * j4 + 1][r] + b.y;
+      float v2 = o[4 * j4 + 2][r] + b.z, v3 = o[4 * j4 + 3][r] + b.w;
+      o[4 * j4 + 0][r] = ACT ? tanh_fast(v0) : v0;
+      o[4 * j4 + 1][r] = ACT ? tanh_fast(v1) : v1;
+      o[4 * j4 + 2][r] = ACT ? tanh_fast(v2) : v2;
+      o[4 * j4 + 3][r] = ACT ? tanh_fast(v3) : v3;
+    }
+  }
+}
+
+template <int R, int IN, int OUT, int... Rest>
+struct NetChain {
+  using Shape = NetShape<IN, OUT, Rest...>;
+  static constexpr int NPARAMS = Shape::NPARAMS;
+  static constexpr int LAST = Shape::LAST;
+  __device__ __forceinline__ static void forward(const float *__restrict__ sw, const float (&a)[IN][R], float (&out)[LAST][R]) {
+    if constexpr (sizeof...(Rest) == 0) {
+      dense_layer<R, IN, OUT, false>(sw, a, out);
+    } else {
+      float h[OUT][R];
+      dense_layer<R, IN, OUT, true>(sw, a, h);
+      NetChain<R, OUT, Rest...>::forward(sw + IN * OUT + OUT, h, out);
+    }
+  }
+};
+
+// Dynamics policies consumed by rollout_kernel: deriv() maps [roll, u_x, u_y, yaw_rate, steer,
+// throttle] to d/dt [roll, u_x, u_y, yaw_rate] for R rollouts.
+template <int R_, int... W>
+struct NeuralNetDyn {
+  static constexpr int R = R_;
+  static constexpr int SMEM_FLOATS = NetShape<W...>::NPARAMS;
+  using Chain = NetChain<R_, W...>;
+  static_assert(NetShape<W...>::FIRST == 6 && NetShape<W...>::LAST == 4, "6 inputs, 4 outputs");
+  __device__ __forceinline__ static void deriv(const float *__restrict__ sw, const float (&in)[6][R_], float (&out)[4][R_]) {
+    Chain::forward(sw, in, out);
+  }
+};
+
+struct CarBasisDyn {
+  static constexpr int R = 1;
+  static constexpr int SMEM_FLOATS = 100;  // theta 4 x 25 row-major
+  __device__ __forceinline__ static void deriv(const float *__restrict__ sw, const float (&in)[6][1], float (&out)[4][1]) {
+    const float roll = in[0][0], vx = in[1][0], vy = in[2][0], wz = in[3][0], steer = in[4][0], thr = in[5][0];
+    const bool moving = vx >= 0.1f;  // (double)vx > .1  <=>  vx >= 0.1f because 0.1f > 0.1
+    const float ratio_y = __fdiv_rn(vy, vx);
+    // front: tan(atan(vy/vx + .45 wz/vx) - steer); rear: vy/vx - .35 wz/vx
+    const float front_arg = moving ? (ratio_y + 0.45f * wz / vx) : 0.0f;
+    const float tf = moving ? tanf(atanf(front_arg) - steer) : tanf(-steer);
+    const float rear = ratio_y - 0.35f * wz / vx;
+    const float ss = sinf(steer);
+    float phi[25];
+    phi[0] = thr;
+    phi[1] = vx / 10.0f;
+    phi[2] = ss * tf / 1200.0f;
+    phi[3] = ss * tf * fabsf(tf) / 1440000.0f;
+    phi[4] = ss * (tf * tf * tf) / 1728000000.0f;
+    phi[5] = wz * vy / 25.0f;
+    phi[6] = wz / 10.0f;
+    phi[7] = vy / 10.0f;
+    phi[8] = ss;
+    phi[9] = moving ? ratio_y / 40.0f : 0.0f;
+    phi[10] = tf / 1400.0f;
+    phi[11] = tf * fabsf(tf) / 1960000.0f;
+    phi[12] = (tf * tf * tf) / 2744000000.0f;
+    phi[13] = moving ? rear / 40.0f : 0.0f;
+    phi[14] = moving ? rear * fabsf(rear) / 1600.0f : 0.0f;
+    phi[15] = moving ? (rear * rear * rear) / 64000.0f : 0.0f;
+    phi[16] = wz * vx / 50.0f;
+    phi[17] = roll;
+    phi[18] = roll * wz;
+    phi[19] = roll * vx / 3.0f;
+    phi[20] = roll * vx * wz / 5.0f;
+    phi[21] = vx * vx / 100.0f;
+    phi[22] = vx * vx * vx / 1000.0f;
+    phi[23] = thr * thr;
+    phi[24] = thr * thr * thr;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      float acc = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 25; i++) acc = fmaf(sw[j * 25 + i], phi[i], acc);
+      out[j][0] = acc;
+    }
+  }
+};
+
+}  // namespace mppi

@@ -1,0 +1,154 @@
+// rollout.cuh -- the fused rollout kernel: control perturbation, clamp, running-mean cost, dynamics,
+// Euler step and crash bookkeeping for T sequential steps, entirely in registers.
+// Replaces rolloutKernel (PI/mppi_controller.cu:72-184) and the device members it calls
+// (PI/neural_net_model.cu:311-410, PI/generalized_linear.cu:168-245, PI/costs.cu:301-409).
+#pragma once
+#include "device_common.cuh"
+#include "dynamics.cuh"
+
+namespace mppi {
+
+// MPPICosts::computeCost (PI/costs.cu:396-409) with its parts (:307-393).  The track cost runs
+// before the crash cost, so a boundary hit is charged in the same step; `crash` is sticky.
+__device__ __forceinline__ float running_cost_step(const DevCostParams &cp, cudaTextureObject_t tex,
+                                                   const float (&s)[S_DIM], float u0, float u1, float du0,
+                                                   float du1, float nu0, float nu1, int &crash) {
+  // control cost (:307-313)
+  float control = 0.0f;
+  control = __fadd_rn(control, __fdiv_rn(__fmul_rn(__fmul_rn(cp.steering_coeff, du0), __fsub_rn(u0, du0)), __fmul_rn(nu0, nu0)));
+  control = __fadd_rn(control, __fdiv_rn(__fmul_rn(__fmul_rn(cp.throttle_coeff, du1), __fsub_rn(u1, du1)), __fmul_rn(nu1, nu1)));
+  // track cost (:359-393): front/back of the car with the fast intrinsics the reference uses
+  const float cy = __cosf(s[2]), sy = __sinf(s[2]);
+  const float xf = fmaf(0.5f, cy, s[0]), yf = fmaf(0.5f, sy, s[1]);
+  const float xb = fmaf(-0.5f, cy, s[0]), yb = fmaf(-0.5f, sy, s[1]);
+  float uu = __fadd_rn(fmaf(cp.c1x, xf, __fmul_rn(cp.c2x, yf)), cp.tx);
+  float vv = __fadd_rn(fmaf(cp.c1y, xf, __fmul_rn(cp.c2y, yf)), cp.ty);
+  float ww = __fadd_rn(fmaf(cp.c1z, xf, __fmul_rn(cp.c2z, yf)), cp.tz);
+  const float front = tex2D<float>(tex, __fdiv_rn(uu, ww), __fdiv_rn(vv, ww));
+  uu = __fadd_rn(fmaf(cp.c1x, xb, __fmul_rn(cp.c2x, yb)), cp.tx);
+  vv = __fadd_rn(fmaf(cp.c1y, xb, __fmul_rn(cp.c2y, yb)), cp.ty);
+  ww = __fadd_rn(fmaf(cp.c1z, xb, __fmul_rn(cp.c2z, yb)), cp.tz);
+  const float back = tex2D<float>(tex, __fdiv_rn(uu, ww), __fdiv_rn(vv, ww));
+  float track = __fmul_rn(__fadd_rn(fabsf(front), fabsf(back)), 0.5f);  // "/2.0" in double is exact
+  track = (fabsf(track) < cp.track_slop) ? 0.0f : __fmul_rn(cp.track_coeff, track);
+  if (front >= cp.boundary_threshold || back >= cp.boundary_threshold) crash = 1;
+  // speed cost (:315-326)
+  const float err = __fsub_rn(s[4], cp.desired_speed);
+  const float sc = cp.l1_cost ? fabsf(err) : __fmul_rn(err, err);
+  const float speed = __fmul_rn(cp.speed_coeff, sc);
+  // crash cost (:328-335, :402)
+  const float crash_cost = crash > 0 ? cp.crash_cost_on : 0.0f;
+  // stabilizing cost (:337-349); the reference compares |u_x| against the double 0.001
+  float stab = 0.0f;
+  if (fabsf(s[4]) >= 0.001f) {  // |u_x| > 0.001 (double)  <=>  |u_x| >= 0.001f because 0.001f > 0.001
+    const float slip = -atanf(__fdiv_rn(s[5], fabsf(s[4])));
+    stab = __fmul_rn(cp.slip_penalty, __fmul_rn(slip, slip));
+    if (fabsf(slip) > cp.max_slip_ang) stab = __fadd_rn(stab, cp.crash_coeff);
+  }
+  float cost = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(control, speed), crash_cost), track), stab);
+  if (cost > 1e12f || isnan(cost)) cost = 1e12f;
+  return cost;
+}
+
+// One thread owns DYN::R consecutive rollouts.  Grid covers B * n_local rollouts; n_local is a
+// multiple of 64, so a warp never straddles two controllers and is either fully valid or idle.
+template <class DYN, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ RolloutParams p) {
+  constexpr int R = DYN::R;
+  extern __shared__ float4 smem4[];
+  float *sw = reinterpret_cast<float *>(smem4);
+  for (int i = threadIdx.x; i < DYN::SMEM_FLOATS / 4; i += BLOCK) smem4[i] = reinterpret_cast<const float4 *>(p.theta_t)[i];
+  __syncthreads();
+
+  const long long total = (long long)p.B * p.n_local;
+  const long long g0 = ((long long)blockIdx.x * BLOCK + threadIdx.x) * R;
+  const bool valid = g0 < total;
+  unsigned int best = 0xffffffffu;
+  int ctrl = 0;
+  if (valid) {
+    ctrl = (int)(g0 / p.n_local);
+    const int lr0 = (int)(g0 - (long long)ctrl * p.n_local);
+    const float *inbox = p.inbox + (size_t)ctrl * p.inbox_stride;
+    const float2 *U = reinterpret_cast<const float2 *>(inbox + INBOX_U);
+    float s[R][S_DIM];
+    float running[R];
+    int crash[R];
+    bool noise_free[R], pure_noise[R];
+    float2 *row[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+#pragma unroll
+      for (int k = 0; k < S_DIM; k++) s[r][k] = inbox[INBOX_STATE + k];
+      running[r] = 0.0f;
+      crash[r] = 0;
+      const int rg = p.r_begin + lr0 + r;  // global rollout index drives the bookkeeping (R2)
+      noise_free[r] = (rg == 0);
+      pure_noise[r] = (rg >= p.pure_noise_from);
+      row[r] = reinterpret_cast<float2 *>(p.du) + (size_t)(g0 + r) * p.T;
+    }
+    for (int i = 0; i < p.T; i++) {
+      const float2 Ui = U[i];
+      float in[6][R];
+      float du[R][2], u[R][2];
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        // PI/mppi_controller.cu:130-155
+        const float2 e = row[r][i];
+        if (noise_free[r] || i < p.opt_delay) {
+          du[r][0] = 0.0f; du[r][1] = 0.0f;
+          u[r][0] = Ui.x; u[r][1] = Ui.y;
+        } else if (pure_noise[r]) {
+          du[r][0] = __fmul_rn(e.x, p.nu0); du[r][1] = __fmul_rn(e.y, p.nu1);
+          u[r][0] = du[r][0]; u[r][1] = du[r][1];
+        } else {
+          du[r][0] = __fmul_rn(e.x, p.nu0); du[r][1] = __fmul_rn(e.y, p.nu1);
+          u[r][0] = __fadd_rn(Ui.x, du[r][0]); u[r][1] = __fadd_rn(Ui.y, du[r][1]);
+        }
+        row[r][i] = make_float2(u[r][0], u[r][1]);  // un-clamped write-back (:153)
+        // enforceConstraints, PI/neural_net_model.cu:311-323
+        u[r][0] = u[r][0] < p.lo0 ? p.lo0 : (u[r][0] > p.hi0 ? p.hi0 : u[r][0]);
+        u[r][1] = u[r][1] < p.lo1 ? p.lo1 : (u[r][1] > p.hi1 ? p.hi1 : u[r][1]);
+        if (i > 0) {
+          // running mean of the step costs, PI/mppi_controller.cu:162-165: float difference,
+          // double divide (by a tabulated reciprocal) and double accumulate, float store.
+          const float c = running_cost_step(p.cp, p.tex, s[r], u[r][0], u[r][1], du[r][0], du[r][1], p.nu0, p.nu1, crash[r]);
+          running[r] = (float)((double)running[r] + (double)__fsub_rn(c, running[r]) * p.inv_step[i]);
+        }
+        in[0][r] = s[r][3]; in[1][r] = s[r][4]; in[2][r] = s[r][5]; in[3][r] = s[r][6];
+        in[4][r] = u[r][0]; in[5][r] = u[r][1];
+      }
+      float dyn_out[4][R];
+      DYN::deriv(sw, in, dyn_out);
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        // kinematics, PI/neural_net_model.cu:346-355 (precise sinf/cosf)
+        float sn, cs;
+        sincosf(s[r][2], &sn, &cs);
+        const float d0 = fmaf(cs, s[r][4], -__fmul_rn(sn, s[r][5]));
+        const float d1 = fmaf(sn, s[r][4], __fmul_rn(cs, s[r][5]));
+        const float d2 = p.negate_yaw ? -s[r][6] : s[r][6];
+        // incrementState, PI/neural_net_model.cu:334-344
+        s[r][0] = fmaf(d0, p.dt, s[r][0]);
+        s[r][1] = fmaf(d1, p.dt, s[r][1]);
+        s[r][2] = fmaf(d2, p.dt, s[r][2]);
+#pragma unroll
+        for (int k = 0; k < 4; k++) s[r][3 + k] = fmaf(dyn_out[k][r], p.dt, s[r][3 + k]);
+        // getCrash, PI/costs.cu:301-305 (the reference compares against the double 1.57)
+        if (fabsf(s[r][3]) >= 1.57f) crash[r] = 1;  // > 1.57 (double)  <=>  >= 1.57f because 1.57f > 1.57
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      p.costs[g0 + r] = running[r];  // + terminalCost == 0 (PI/costs.cu:411-414)
+      p.crash[g0 + r] = (unsigned char)crash[r];
+      const unsigned int o = float_to_ordered(running[r]);
+      best = o < best ? o : best;
+    }
+  }
+  // min-cost baseline (host loop at PI/mppi_controller.cu:627-632): one redux + one atomic per warp
+  const unsigned int wbest = __reduce_min_sync(0xffffffffu, best);
+  const int wctrl = __shfl_sync(0xffffffffu, ctrl, 0);
+  if ((threadIdx.x & 31) == 0 && wbest != 0xffffffffu) atomicMin(p.baseline + wctrl, wbest);
+}
+
+}  // namespace mppi

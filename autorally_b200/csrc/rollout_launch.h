@@ -1,0 +1,17 @@
+// rollout_launch.h -- host-side launchers of the rollout-kernel instantiations.  Each lives in its own
+// translation unit (rollout_*.cu) so the variants compile in parallel.
+#pragma once
+#include "device_common.cuh"
+
+namespace mppi {
+
+// `small` selects 32-thread CTAs so that a few thousand rollouts still spread over many SMs.
+cudaError_t launch_rollout_nn32_r1(const RolloutParams &p, cudaStream_t st, bool small);
+cudaError_t launch_rollout_nn32_r2(const RolloutParams &p, cudaStream_t st, bool small);
+cudaError_t launch_rollout_nn64_r1(const RolloutParams &p, cudaStream_t st, bool small);
+cudaError_t launch_rollout_bf(const RolloutParams &p, cudaStream_t st, bool small);
+
+template <class DYN, int BLOCK>
+struct RolloutLauncher;
+
+}  // namespace mppi

@@ -1,0 +1,324 @@
+// weighting.cuh -- the Philox control-noise sampler, the importance-weighting reduction and the
+// finalisation (control update, Savitzky-Golay smoothing, nominal trajectory).
+//
+// Replaces curandGenerateNormal (PI/mppi_controller.cu:612), the host min / normaliser loops
+// (:627-652), normExpKernel (:193-203), weightedReductionKernel (:219-267), savitskyGolay
+// (:468-499) and computeNominalTraj (:501-519).
+#pragma once
+#include "device_common.cuh"
+#include "dynamics.cuh"
+
+namespace mppi {
+
+// ------------------------------------------------------------------------------ sampler ----
+// Philox4x32-10 (Salmon et al., SC'11).  Stream definition: counter = (q, r, call, b)
+// with q the timestep pair (t = 2q, 2q+1), r the GLOBAL rollout index, call the compute-call
+// counter and b the controller; key = seed.  The 4 outputs become eps[r][2q..2q+1][0..1] by
+// Box-Muller, so one thread writes one aligned float4 and a warp writes 512 contiguous bytes.
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ float2 box_muller(uint32_t xa, uint32_t xb) {
+  // radius = sqrt(-2 ln((xa + .5) 2^-32)); angle = 2 pi (xb + .5) 2^-32 - pi
+  const float ua = fmaf((float)xa, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+  const float ang = fmaf((float)xb, 1.4629180792671596e-09f, -3.14159265358979f + 7.3145903963357981e-10f);
+  const float rad = sqrtf(-2.0f * __logf(ua));
+  float sn, cs;
+  __sincosf(ang, &sn, &cs);
+  return make_float2(rad * cs, rad * sn);
+}
+
+__global__ void __launch_bounds__(256) sample_noise_kernel(float *__restrict__ du, int n_local, int r_begin, int T,
+                                                            int B, uint32_t seed_lo, uint32_t seed_hi, uint32_t call) {
+  const int Q = (T + 1) >> 1;
+  const long long total = (long long)B * n_local * Q;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(idx % Q);
+    const long long g = idx / Q;
+    const int lr = (int)(g % n_local), b = (int)(g / n_local);
+    uint32_t x[4];
+    philox4x32_10((uint32_t)q, (uint32_t)(r_begin + lr), call, (uint32_t)b, seed_lo, seed_hi, x);
+    const float2 z0 = box_muller(x[0], x[1]), z1 = box_muller(x[2], x[3]);
+    float *dst = du + ((size_t)g * T + 2 * q) * C_DIM;
+    if ((T & 1) == 0) {
+      *reinterpret_cast<float4 *>(dst) = make_float4(z0.x, z0.y, z1.x, z1.y);
+    } else {
+      dst[0] = z0.x; dst[1] = z0.y;
+      if (2 * q + 1 < T) { dst[2] = z1.x; dst[3] = z1.y; }
+    }
+  }
+}
+
+// -------------------------------------------------------------------- weighting reduction ----
+// Shard partial record per controller: [0] baseline b, [1] Z = sum exp(-gamma (c - b)),
+// [2] Q = sum exp(..)^2, [3] unused, [4 .. 4+2T) W[t][j] = sum exp(..) * V[r][t][j].
+constexpr int SHARD_HDR = 4;
+
+struct WeightParams {
+  const float *costs;            // [B][n_local]
+  const float2 *V;               // [B][n_local][T]
+  const unsigned int *baseline;  // [B]
+  float *block_partials;         // [B][nblk][shard_floats]
+  float *shard;                  // [B][shard_floats]
+  unsigned int *done_counter;    // [B]
+  int n_local, T, nblk, rows_per_blk, shard_floats;
+  float gamma;
+};
+
+// grid (nblk, B), block 256.  Each CTA owns rows_per_blk rollouts of one controller: it turns their
+// costs into weights in shared memory (exp-normalisation against the baseline the rollout kernel
+// left behind), block-reduces Z and Q with warp shuffles, and streams the rows' sampled controls once,
+// coalesced (each row is T contiguous float2), accumulating the weighted sum per column.  The last
+// CTA of a controller to finish (atomic ticket) adds the per-CTA partials in fixed order, so results
+// are bitwise reproducible run to run.
+__global__ void __launch_bounds__(256) weight_reduce_kernel(const __grid_constant__ WeightParams p) {
+  extern __shared__ float sm[];
+  float *w = sm;                               // [rows_per_blk]
+  float2 *colsum = reinterpret_cast<float2 *>(sm + ((p.rows_per_blk + 3) & ~3));  // [nrl][T]
+  __shared__ float red[2][8];
+  __shared__ bool is_last;
+  const int b = blockIdx.y, blk = blockIdx.x, tid = threadIdx.x;
+  const int r0 = blk * p.rows_per_blk;
+  const int nrows = min(p.rows_per_blk, p.n_local - r0);
+  const float base = ordered_to_float(p.baseline[b]);
+  const float *costs = p.costs + (size_t)b * p.n_local + r0;
+  float z = 0.0f, q = 0.0f;
+  for (int i = tid; i < nrows; i += 256) {
+    const float wi = expf(-p.gamma * (costs[i] - base));  // normExpKernel (:200-201)
+    w[i] = wi;
+    z += wi;
+    q = fmaf(wi, wi, q);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    z += __shfl_xor_sync(0xffffffffu, z, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if ((tid & 31) == 0) { red[0][tid >> 5] = z; red[1][tid >> 5] = q; }
+  __syncthreads();
+  // weighted column sums: thread (rl, c) walks rows rl, rl+nrl, ... of column c
+  const int T = p.T;
+  const int nrl = max(1, 256 / T);
+  const float2 *V = p.V + ((size_t)b * p.n_local + r0) * T;
+  for (int c0 = 0; c0 < T; c0 += 256) {  // one pass when T <= 256
+    const int rl = (T <= 256) ? tid / T : 0;
+    const int c = (T <= 256) ? tid - rl * T : c0 + tid;
+    float2 acc = make_float2(0.0f, 0.0f);
+    if (rl < nrl && c < T) {
+      int i = rl;
+      for (; i + 3 * nrl < nrows; i += 4 * nrl) {
+        const float2 v0 = V[(size_t)i * T + c], v1 = V[(size_t)(i + nrl) * T + c];
+        const float2 v2 = V[(size_t)(i + 2 * nrl) * T + c], v3 = V[(size_t)(i + 3 * nrl) * T + c];
+        acc.x = fmaf(w[i], v0.x, acc.x); acc.y = fmaf(w[i], v0.y, acc.y);
+        acc.x = fmaf(w[i + nrl], v1.x, acc.x); acc.y = fmaf(w[i + nrl], v1.y, acc.y);
+        acc.x = fmaf(w[i + 2 * nrl], v2.x, acc.x); acc.y = fmaf(w[i + 2 * nrl], v2.y, acc.y);
+        acc.x = fmaf(w[i + 3 * nrl], v3.x, acc.x); acc.y = fmaf(w[i + 3 * nrl], v3.y, acc.y);
+      }
+      for (; i < nrows; i += nrl) {
+        const float2 v = V[(size_t)i * T + c];
+        acc.x = fmaf(w[i], v.x, acc.x); acc.y = fmaf(w[i], v.y, acc.y);
+      }
+      colsum[rl * T + c] = acc;
+    }
+    if (T > 256) {
+      if (c < T) reinterpret_cast<float2 *>(p.block_partials + ((size_t)b * p.nblk + blk) * p.shard_floats + SHARD_HDR)[c] = acc;
+    }
+  }
+  __syncthreads();
+  float *out = p.block_partials + ((size_t)b * p.nblk + blk) * p.shard_floats;
+  if (T <= 256 && tid < T) {
+    float2 acc = colsum[tid];
+    for (int rl = 1; rl < nrl; rl++) { acc.x += colsum[rl * T + tid].x; acc.y += colsum[rl * T + tid].y; }
+    reinterpret_cast<float2 *>(out + SHARD_HDR)[tid] = acc;
+  }
+  if (tid == 0) {
+    float zz = 0.0f, qq = 0.0f;
+    for (int i = 0; i < 8; i++) { zz += red[0][i]; qq += red[1][i]; }
+    out[0] = base; out[1] = zz; out[2] = qq; out[3] = 0.0f;
+  }
+  // ---- last CTA of this controller combines the per-CTA partials in fixed order ----
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int ticket = atomicAdd(p.done_counter + b, 1u);
+    is_last = (ticket == (unsigned int)p.nblk - 1);
+    if (is_last) p.done_counter[b] = 0;  // re-arm for the next launch
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const float *parts = p.block_partials + (size_t)b * p.nblk * p.shard_floats;
+  float *shard = p.shard + (size_t)b * p.shard_floats;
+  for (int k = tid; k < p.shard_floats; k += 256) {
+    if (k == 0) { shard[0] = base; continue; }
+    if (k == 3 || k >= SHARD_HDR + 2 * T) { shard[k] = 0.0f; continue; }
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+    int j = 0;
+    for (; j + 3 < p.nblk; j += 4) {
+      a0 += __ldcg(parts + (size_t)j * p.shard_floats + k);
+      a1 += __ldcg(parts + (size_t)(j + 1) * p.shard_floats + k);
+      a2 += __ldcg(parts + (size_t)(j + 2) * p.shard_floats + k);
+      a3 += __ldcg(parts + (size_t)(j + 3) * p.shard_floats + k);
+    }
+    for (; j < p.nblk; j++) a0 += __ldcg(parts + (size_t)j * p.shard_floats + k);
+    shard[k] = (a0 + a1) + (a2 + a3);
+  }
+}
+
+// ------------------------------------------------------------------------------ finalize ----
+struct FinalizeParams {
+  const float *gathered;  // [G][B][shard_floats]
+  float *inbox;           // [B][inbox_stride]  (U is rewritten for the next iteration / resident step)
+  float *outbox;          // [B][outbox_stride]: result[4] | U_smoothed[2T] | U_new[2T] | state_sol[7T] | ctrl_sol[2T]
+  const float *theta_t;   // NN: transposed packed weights; BF: theta 4x25
+  const int *net_structure;
+  int num_layers;         // NN: entries of net_structure; 0 = basis-function model
+  int G, B, T, shard_floats, inbox_stride, outbox_stride;
+  float gamma, dt, lo0, hi0, lo1, hi1;
+  int negate_yaw;
+  int last_iter;          // 1: smooth + nominal trajectory; 0: U <- U_new only (num_iters > 1)
+  int feed_back;          // 1: write the smoothed U back into the inbox (resident stepping)
+};
+
+constexpr int FIN_MAX_WIDTH = 128;
+
+// Host twin of the basis functions for the nominal trajectory (single lane; 100 steps).
+__device__ __forceinline__ void car_basis_host_twin(const float *theta, const float *s, float u0, float u1, float *out4) {
+  float in[6][1] = {{s[3]}, {s[4]}, {s[5]}, {s[6]}, {u0}, {u1}};
+  float o[4][1];
+  CarBasisDyn::deriv(theta, in, o);
+  for (int j = 0; j < 4; j++) out4[j] = o[j][0];
+}
+
+// grid B, block 256.  Combines the G shard records (log-sum-exp rescale),
+// U_new = W / Z (control update :663-667), Savitzky-Golay (:468-499), then warp 0 integrates the
+// nominal trajectory with the host-twin arithmetic (separate multiply and add, precise tanhf/sinf/cosf).
+__global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ FinalizeParams p) {
+  extern __shared__ float fsm[];
+  const int T = p.T, tid = threadIdx.x, b = blockIdx.x;
+  float *Unew = fsm;                 // [2T]
+  float *Usm = Unew + 2 * T;         // [2T]
+  float *act = Usm + 2 * T;          // [2][FIN_MAX_WIDTH]
+  float *sw = act + 2 * FIN_MAX_WIDTH;  // staged parameters
+  __shared__ float scale[64];
+  __shared__ float hdr[4];
+  float *inbox = p.inbox + (size_t)b * p.inbox_stride;
+  float *outbox = p.outbox + (size_t)b * p.outbox_stride;
+
+  if (tid == 0) {
+    float base = p.gathered[((size_t)0 * p.B + b) * p.shard_floats];
+    for (int g = 1; g < p.G; g++) base = fminf(base, p.gathered[((size_t)g * p.B + b) * p.shard_floats]);
+    float Z = 0.0f, Q = 0.0f;
+    for (int g = 0; g < p.G; g++) {
+      const float *rec = p.gathered + ((size_t)g * p.B + b) * p.shard_floats;
+      const float sg = (p.G == 1) ? 1.0f : expf(-p.gamma * (rec[0] - base));
+      scale[g] = sg;
+      Z = fmaf(sg, rec[1], Z);
+      Q = fmaf(sg * sg, rec[2], Q);
+    }
+    hdr[0] = base; hdr[1] = Z; hdr[2] = Q / Z; hdr[3] = 0.0f;
+  }
+  __syncthreads();
+  const float Z = hdr[1];
+  for (int k = tid; k < 2 * T; k += 256) {
+    float wsum = 0.0f;
+    for (int g = 0; g < p.G; g++) wsum = fmaf(scale[g], p.gathered[((size_t)g * p.B + b) * p.shard_floats + SHARD_HDR + k], wsum);
+    Unew[k] = wsum / Z;
+  }
+  if (tid < 4) outbox[tid] = hdr[tid];
+  __syncthreads();
+  for (int k = tid; k < 2 * T; k += 256) outbox[4 + 2 * T + k] = Unew[k];
+  if (!p.last_iter) {
+    for (int k = tid; k < 2 * T; k += 256) inbox[INBOX_U + k] = Unew[k];
+    return;
+  }
+  // Savitzky-Golay: P = [hist0, hist1, U_0 .. U_{T-1}, U_{T-1}, U_{T-1}], taps [-3 12 17 12 -3]/35
+  const float f0 = -3.0f / 35.0f, f1 = 12.0f / 35.0f, f2 = 17.0f / 35.0f;
+  for (int k = tid; k < 2 * T; k += 256) {
+    const int i = k >> 1, j = k & 1;
+    float pv[5];
+#pragma unroll
+    for (int m = 0; m < 5; m++) {
+      const int ii = i + m;  // index into P
+      pv[m] = ii < 2 ? inbox[INBOX_HIST + 2 * ii + j] : (ii < T + 2 ? Unew[2 * (ii - 2) + j] : Unew[2 * (T - 1) + j]);
+    }
+    float acc = __fmul_rn(f0, pv[0]);
+    acc = __fadd_rn(acc, __fmul_rn(f1, pv[1]));
+    acc = __fadd_rn(acc, __fmul_rn(f2, pv[2]));
+    acc = __fadd_rn(acc, __fmul_rn(f1, pv[3]));
+    acc = __fadd_rn(acc, __fmul_rn(f0, pv[4]));
+    Usm[k] = acc;
+    outbox[4 + k] = acc;
+  }
+  // stage the model parameters for the nominal trajectory
+  int nparams = 100;
+  if (p.num_layers > 0) {
+    nparams = 0;
+    for (int l = 0; l + 1 < p.num_layers; l++) nparams += (p.net_structure[l] + 1) * p.net_structure[l + 1];
+  }
+  for (int k = tid; k < nparams; k += 256) sw[k] = p.theta_t[k];
+  __syncthreads();
+  if (p.feed_back)
+    for (int k = tid; k < 2 * T; k += 256) inbox[INBOX_U + k] = Usm[k];
+  if (tid >= 32) return;
+  // ---- nominal trajectory (computeNominalTraj :501-519 -> host updateState) on warp 0 ----
+  const int lane = tid;
+  float s[S_DIM];
+  for (int k = 0; k < S_DIM; k++) s[k] = inbox[INBOX_STATE + k];
+  float *ssol = outbox + 4 + 4 * T;
+  float *csol = ssol + S_DIM * T;
+  for (int i = 0; i < T; i++) {
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < S_DIM; k++) ssol[i * S_DIM + k] = s[k];
+    }
+    float u0 = Usm[2 * i], u1 = Usm[2 * i + 1];
+    u0 = u0 < p.lo0 ? p.lo0 : (u0 > p.hi0 ? p.hi0 : u0);
+    u1 = u1 < p.lo1 ? p.lo1 : (u1 > p.hi1 ? p.hi1 : u1);
+    if (lane == 0) { csol[2 * i] = u0; csol[2 * i + 1] = u1; }
+    float dyn[4];
+    if (p.num_layers > 0) {
+      // lane j computes neurons j, j+32, ... of each layer; activations ping-pong through smem
+      float *cur = act, *nxt = act + FIN_MAX_WIDTH;
+      if (lane == 0) { cur[0] = s[3]; cur[1] = s[4]; cur[2] = s[5]; cur[3] = s[6]; cur[4] = u0; cur[5] = u1; }
+      __syncwarp();
+      const float *W = sw;
+      for (int l = 0; l + 1 < p.num_layers; l++) {
+        const int nin = p.net_structure[l], nout = p.net_structure[l + 1];
+        for (int j = lane; j < nout; j += 32) {
+          float t = 0.0f;
+          for (int k = 0; k < nin; k++) t = __fadd_rn(t, __fmul_rn(W[k * nout + j], cur[k]));
+          t = __fadd_rn(t, W[nin * nout + j]);
+          if (l + 2 < p.num_layers) t = tanhf(t);
+          nxt[j] = t;
+        }
+        __syncwarp();
+        W += (nin + 1) * nout;
+        float *tmp = cur; cur = nxt; nxt = tmp;
+      }
+      for (int k = 0; k < 4; k++) dyn[k] = cur[k];
+      __syncwarp();
+    } else {
+      car_basis_host_twin(sw, s, u0, u1, dyn);
+    }
+    const float cs = cosf(s[2]), sn = sinf(s[2]);
+    const float d0 = __fsub_rn(__fmul_rn(cs, s[4]), __fmul_rn(sn, s[5]));
+    const float d1 = __fadd_rn(__fmul_rn(sn, s[4]), __fmul_rn(cs, s[5]));
+    const float d2 = (p.num_layers == 0 || p.negate_yaw) ? -s[6] : s[6];
+    s[0] = __fadd_rn(s[0], __fmul_rn(d0, p.dt));
+    s[1] = __fadd_rn(s[1], __fmul_rn(d1, p.dt));
+    s[2] = __fadd_rn(s[2], __fmul_rn(d2, p.dt));
+    for (int k = 0; k < 4; k++) s[3 + k] = __fadd_rn(s[3 + k], __fmul_rn(dyn[k], p.dt));
+  }
+}
+
+}  // namespace mppi

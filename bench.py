@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py -- rollout-steps/s of the MPPI hot path (computeControl) on B200.
+
+    python bench.py --gpus 1 --steps 200 --warmup 10            # our CUDA path
+    python bench.py --impl reference --steps 5 --warmup 1       # the reference's CPU path (oracle port)
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one complete computeControl pipeline (Philox noise -> fused rollouts -> importance
+weighting -> Savitzky-Golay -> nominal trajectory) of BASELINE.json configs[1]: path_integral_nn,
+1920 rollouts x 100 timesteps on the synthetic ellipse costmap.  At N > 1 every rank runs one such
+controller (batched-MPC sharding: independent controllers, no communication) for `value`, and the
+1M-rollout configuration sharded over the ranks with one NCCL all-gather per step is reported under
+"sharded_large".  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FLOP_PER_ROLLOUT_STEP_NN = 2756.0  # 2*(6*32+32*32+32*4) + 68 bias adds
+N_ROLLOUTS, T_STEPS = 1920, 100
+LARGE_ROLLOUTS = 1 << 20           # "large-sample MPPI": 1M rollouts (16384 x 64)
+
+
+def load_setup():
+    from autorally_b200.params import make_ellipse_costmap
+    from tests.common import cost_params_for, default_state, warm_controls
+    models = np.load(os.path.join(ROOT, "tests", "golden", "ref_models.npz"))
+    costmap = make_ellipse_costmap()
+    cp = cost_params_for(costmap)
+    return models, costmap, cp, default_state(5.0), warm_controls(T_STEPS)
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index=0, period=0.05):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        self.index, self.period = index, period
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def __enter__(self):
+        if self.nv:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thread:
+            self._thread.join()
+
+    def summary(self):
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_baseline(models, costmap, cp, state, U, budget_s=12.0):
+    """The CPU restatement (oracle port) on the host's cores: full computeControl, all threads."""
+    from tests.common import make_oracle
+    o = make_oracle("nn", models, costmap, cp)
+    cores = os.cpu_count() or 1
+    eps = np.random.default_rng(0).standard_normal((1, N_ROLLOUTS, T_STEPS, 2)).astype(np.float32)
+    o.compute_control(state, U, np.zeros(4), [0.275, 0.3], eps, threads=cores)
+    times = []
+    t_end = time.perf_counter() + budget_s
+    while time.perf_counter() < t_end and len(times) < 30:
+        t0 = time.perf_counter()
+        o.compute_control(state, U, np.zeros(4), [0.275, 0.3], eps, threads=cores)
+        times.append(time.perf_counter() - t0)
+    med = statistics.median(times)
+    out = {"value": N_ROLLOUTS * T_STEPS / med, "unit": "rollout-steps/s", "cores": cores, "kind": "port",
+           "sample": "%d x computeControl(1920x100), oracle/mppi_oracle.c, %d pthreads, median" % (len(times), cores)}
+    # single-thread straight loop and the ml_pipeline-style torch float64 model (dynamics only)
+    t0 = time.perf_counter()
+    o.dynamics_rollouts(state, U, [0.275, 0.3], eps[0][:480])
+    out["dynamics_only_1thread"] = 480 * T_STEPS / (time.perf_counter() - t0)
+    try:
+        import torch
+        from autorally_b200.params import unpack_nn_params
+        ws, bs = unpack_nn_params(models["autorally_nnet_theta"], models["autorally_nnet_structure"])
+        torch.set_num_threads(cores)
+        layers = []
+        for i, (w, b) in enumerate(zip(ws, bs)):
+            lin = torch.nn.Linear(w.shape[1], w.shape[0]).double()
+            lin.weight.data = torch.from_numpy(np.asarray(w, np.float64))
+            lin.bias.data = torch.from_numpy(np.asarray(b, np.float64))
+            layers.append(lin)
+            if i < len(ws) - 1:
+                layers.append(torch.nn.Tanh())
+        net = torch.nn.Sequential(*layers)
+        s = torch.from_numpy(np.broadcast_to(state.astype(np.float64), (N_ROLLOUTS, 7)).copy())
+        u = torch.from_numpy(np.broadcast_to(U.astype(np.float64), (N_ROLLOUTS, T_STEPS, 2)).copy())
+
+        def roll():
+            x = s.clone()
+            with torch.no_grad():
+                for t in range(T_STEPS):
+                    y = net(torch.cat([x[:, 3:7], u[:, t]], 1))
+                    der = torch.stack([torch.cos(x[:, 2]) * x[:, 4] - torch.sin(x[:, 2]) * x[:, 5],
+                                       torch.sin(x[:, 2]) * x[:, 4] + torch.cos(x[:, 2]) * x[:, 5], -x[:, 6]], 1)
+                    x = x + torch.cat([der, y], 1) * 0.02
+            return x
+        roll()
+        tt = []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            roll()
+            tt.append(time.perf_counter() - t0)
+        out["torch_f64_dynamics_only"] = N_ROLLOUTS * T_STEPS / statistics.median(tt)
+    except Exception as e:  # pragma: no cover
+        out["torch_f64_dynamics_only"] = "unavailable: %r" % (e,)
+    return out
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port; the reference's C++/CUDA cannot be built
+    here) on the box's host cores; under torchrun only rank 0 works."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    models, costmap, cp, state, U = load_setup()
+    from tests.common import make_oracle
+    o = make_oracle("nn", models, costmap, cp)
+    cores = os.cpu_count() or 1
+    rng = np.random.default_rng(0)
+    eps = rng.standard_normal((1, N_ROLLOUTS, T_STEPS, 2)).astype(np.float32)
+    Uc = U.copy()
+    for _ in range(args.warmup):
+        Uc = o.compute_control(state, Uc, np.zeros(4), [0.275, 0.3], eps, threads=cores)["U"]
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        Uc = o.compute_control(state, Uc, np.zeros(4), [0.275, 0.3], eps, threads=cores)["U"]
+    dt = time.perf_counter() - t0
+    val = N_ROLLOUTS * T_STEPS * args.steps / dt
+    line = {"impl": "reference", "metric": "rollout-steps/sec", "value": val, "unit": "rollout-steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "path_integral_nn 1920 rollouts x 100 steps, ellipse costmap (CPU, host cores)"},
+            "cpu_baseline": {"value": val, "unit": "rollout-steps/s", "cores": cores, "kind": "port",
+                             "sample": "%d x full computeControl on %d pthreads" % (args.steps, cores)},
+            "e2e": {"value": val, "unit": "rollout-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def measure_large(models, costmap, cp, state, U, n_rollouts, r_begin=0, r_count=0, steps=3, fp32_peak=None, hbm_peak=None):
+    from tests.common import make_context
+    out = {}
+    with make_context("nn", models, costmap, cp, n_rollouts, rollout_begin=r_begin, rollout_count=r_count) as ctx:
+        ctx.compute_control(state, U)
+        ctx.run_resident(1)
+        ms, rk = ctx.run_resident(steps, time_rollout=True)
+        n_local = ctx.n_local
+        out.update(rollouts=n_local, steps=steps, ms_per_step=ms / steps, rollout_kernel_ms=rk / steps,
+                   value=n_local * T_STEPS * steps / (ms * 1e-3), variant=ctx.resolved_variant())
+        tf = FLOP_PER_ROLLOUT_STEP_NN * n_local * T_STEPS / (rk / steps * 1e-3) / 1e12
+        out["rollout_tflops"] = tf
+        if fp32_peak:
+            out["rollout_frac_of_fp32_peak"] = tf / fp32_peak
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-large", action="store_true", help="skip the 1M-rollout section")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    from autorally_b200 import capi
+    from tests.common import make_context
+    models, costmap, cp, state, U = load_setup()
+    fp32_peak = capi.measure_fp32_peak()
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    hbm_peak, hbm_src = 6650.0, "fallback"
+    if os.path.exists(peaks_path):
+        hbm_peak, hbm_src = json.load(open(peaks_path)).get("hbm_gbs", 6650.0), "measured"
+
+    ctx = make_context("nn", models, costmap, cp, N_ROLLOUTS, device=local_rank)
+    out = ctx.compute_control(state, U)  # initialises the device-resident state / U
+    # ---- device-resident throughput (value): L2 flushed between timed steps ----
+    ctx.run_resident(args.warmup, flush_l2=True)
+    barrier()
+    with ClockSampler(local_rank) as clk:
+        ms, rk = ctx.run_resident(args.steps, time_rollout=True, flush_l2=True)
+    barrier()
+    launches = ctx.last_launch_count()
+    ms = max_over_ranks(ms)
+    value = world * N_ROLLOUTS * T_STEPS * args.steps / (ms * 1e-3)
+    # warm-L2 figure (how the controller actually runs: same buffers every call)
+    ctx.run_resident(args.warmup)
+    ms_warm, _ = ctx.run_resident(args.steps)
+    # ---- end to end through the C ABI with host buffers (e2e) + latency percentiles ----
+    Uc = U.copy()
+    hist = np.zeros(4, np.float32)
+    for _ in range(args.warmup):
+        Uc = ctx.compute_control(state, Uc, hist)["U"]
+    lat = []
+    barrier()
+    t_all = time.perf_counter()
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        Uc = ctx.compute_control(state, Uc, hist)["U"]
+        lat.append(time.perf_counter() - t0)
+    e2e_s = max_over_ranks(time.perf_counter() - t_all)
+    e2e_launches = ctx.last_launch_count() * args.steps
+    lat.sort()
+    e2e = {"value": world * N_ROLLOUTS * T_STEPS * args.steps / e2e_s, "unit": "rollout-steps/s",
+           "h2d_bytes_per_step": int(4 * (12 + 2 * T_STEPS)), "d2h_bytes_per_step": int(4 * (4 + 13 * T_STEPS)),
+           "p50_ms": 1e3 * lat[len(lat) // 2], "p99_ms": 1e3 * lat[min(len(lat) - 1, int(0.99 * len(lat)))]}
+    rollout_ms = rk / args.steps
+    achieved = FLOP_PER_ROLLOUT_STEP_NN * N_ROLLOUTS * T_STEPS / (rollout_ms * 1e-3) / 1e12
+    roofline = {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
+                "traffic": None, "kernel": "rollout_kernel", "kernel_ms": rollout_ms,
+                "note": "FP32 FFMA issue bound (CUDA cores; neither HBM nor tensor); peak = FFMA microbenchmark measured in this run; "
+                        "1920 rollouts occupy <2% of the machine, see 'large' for the filled-GPU fraction"}
+    line = {"metric": "rollout-steps/sec", "value": value, "unit": "rollout-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "path_integral_nn: NeuralNetModel<7,2,3,6,32,32,4>, 1920 rollouts x 100 steps, ellipse costmap, "
+                                   "one controller per GPU", "rollouts": N_ROLLOUTS, "timesteps": T_STEPS,
+                       "l2": "flushed between timed steps (256 MiB memset outside the timed intervals)",
+                       "variant": ctx.resolved_variant(), "parallelism": "independent controllers x%d" % world},
+            "ms_per_step_warm_l2": ms_warm / args.steps, "e2e": e2e, "gpu_launches": launches + e2e_launches,
+            "roofline": roofline, "clocks": clk.summary(), "fp32_peak_tflops_measured": fp32_peak,
+            "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src,
+            "trajectory_cost": float(out["trajectory_cost"])}
+    ctx.close()
+    if not args.no_large:
+        if world == 1:
+            line["large"] = measure_large(models, costmap, cp, state, U, LARGE_ROLLOUTS, fp32_peak=fp32_peak)
+        else:
+            line["sharded_large"] = run_sharded_large(models, costmap, cp, state, U, world, rank, local_rank, barrier, max_over_ranks)
+    if rank == 0 and world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline(models, costmap, cp, state, U)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_sharded_large(models, costmap, cp, state, U, world, rank, local_rank, barrier, max_over_ranks, steps=5):
+    """configs[3]: 1M rollouts x 100 steps sharded over the ranks; one NCCL all-gather of the
+    3+2T-float partial record per step."""
+    import torch
+    import torch.distributed as dist
+    from tests.common import make_context
+    from tests.test_parity_gpu import ctypes_float_array
+    chunks = LARGE_ROLLOUTS // 64
+    lo, hi = chunks * rank // world * 64, chunks * (rank + 1) // world * 64
+    ctx = make_context("nn", models, costmap, cp, LARGE_ROLLOUTS, rollout_begin=lo, rollout_count=hi - lo, device=local_rank)
+    sf = ctx.shard_floats()
+    mine = ctypes_float_array(ctx.shard_partials_ptr(), sf)
+    gathered = torch.empty((world, sf), dtype=torch.float32, device="cuda")
+    Uc = U.copy()
+
+    def step(Uc):
+        ctx.shard_begin(state, Uc)
+        dist.all_gather_into_tensor(gathered.view(-1), mine)
+        torch.cuda.current_stream().synchronize()
+        return ctx.shard_finish(gathered.data_ptr(), world)["U"]
+    for _ in range(2):
+        Uc = step(Uc)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        Uc = step(Uc)
+    barrier()
+    dt = max_over_ranks(time.perf_counter() - t0)
+    ctx.close()
+    return {"rollouts": LARGE_ROLLOUTS, "steps": steps, "ms_per_step": 1e3 * dt / steps,
+            "value": LARGE_ROLLOUTS * T_STEPS * steps / dt, "unit": "rollout-steps/s",
+            "exchange": "all_gather of %d floats per rank per step (NCCL)" % sf, "timing": "host wall clock incl. H2D/D2H, max over ranks"}
+
+
+if __name__ == "__main__":
+    main()
