@@ -179,13 +179,21 @@ static void state_deriv(const oracle_dynamics *d, const float *s, const float *u
 
 /* ------------------------------------------------------------------ costs ---- */
 
-/* CUDA texture fetch, normalised coordinates, point filter, clamp (PI/costs.cu:143-149):
- * texel = clamp(floor(coord * dim), 0, dim-1). */
+/* CUDA texture fetch, normalised coordinates, point filter, clamp (PI/costs.cu:143-149).  The texture
+ * unit is third-party arithmetic; its texel selection was measured on B200
+ * with tools/texprobe.cu (63 758 probes at and around every texel boundary of 5 widths, 0 mismatches,
+ * profiles/texprobe_r01.txt): the normalised coordinate is TRUNCATED to 21 fractional bits, then
+ * texel = clamp(floor(coord_q * dim), 0, dim-1).  A plain floorf(u * W) differs exactly at texel
+ * boundaries, which grid-aligned start poses hit systematically. */
+static int tex_index(float coord, int dim) {
+  if (!(coord > 0.0f)) return 0; /* negative, zero and NaN clamp to texel 0 */
+  double q = floor((double)coord * 2097152.0) / 2097152.0;
+  double t = floor(q * (double)dim);
+  return t >= (double)dim ? dim - 1 : (int)t;
+}
+
 static float tex_lookup(const oracle_costmap *m, float un, float vn) {
-  float fx = floorf(un * (float)m->width), fy = floorf(vn * (float)m->height);
-  int ix = (fx >= 0.0f) ? ((fx >= (float)m->width) ? m->width - 1 : (int)fx) : 0;   /* NaN -> 0 */
-  int iy = (fy >= 0.0f) ? ((fy >= (float)m->height) ? m->height - 1 : (int)fy) : 0;
-  return m->channel0[(size_t)iy * m->width + ix];
+  return m->channel0[(size_t)tex_index(vn, m->height) * m->width + tex_index(un, m->width)];
 }
 
 static void coor_transform(const oracle_cost_params *p, float x, float y, float *u, float *v, float *w) {
