@@ -73,7 +73,7 @@ def build_host_tests(force=False):
         deps += [os.path.join(d, f) for f in fs]
     if not force and os.path.exists(out) and os.path.getmtime(out) >= _newest(deps):
         return out
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-I", inc, src, "-o", out, "-L", LIB_DIR, "-lmppi_b200",
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-I", inc, "-I", os.path.join(inc, "compat"), src, "-o", out, "-L", LIB_DIR, "-lmppi_b200",
                                     "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"]
     subprocess.check_call(cmd)
     return out
