@@ -84,6 +84,86 @@ struct NetChain {
   }
 };
 
+// ---- packed variant: two rollouts per thread in f32x2 registers ---------------------------------
+// sm_100 has a 2-wide FP32 FMA (PTX fma.rn.f32x2, SASS FFMA2) whose second source may be a single
+// 32-bit register or uniform register broadcast to both halves.  With the two rollouts of a thread
+// packed as (r0, r1) the scalar weight broadcasts for free, the FMA issue slots halve, and each half
+// still accumulates k ascending with FMA, bias last -- bit-identical to the scalar layer.
+// WSRC: 0 = weights from shared memory (LDS.128), 1 = from the constant bank (LDCU.128 -> uniform regs).
+#ifndef MPPI_CONST_THETA_FLOATS
+#define MPPI_CONST_THETA_FLOATS 1412
+#endif
+__constant__ float c_theta[MPPI_CONST_THETA_FLOATS];
+
+template <int WSRC>
+__device__ __forceinline__ float4 load_w4(const float *__restrict__ sw, int const_off, int idx4) {
+  if constexpr (WSRC == 0) return reinterpret_cast<const float4 *>(sw)[idx4];
+  else return reinterpret_cast<const float4 *>(c_theta + const_off)[idx4];
+}
+
+template <int IN, int OUT, bool ACT, int WSRC>
+__device__ __forceinline__ void dense_layer_p2(const float *__restrict__ sw, int const_off, const float2 (&a)[IN], float2 (&o)[OUT]) {
+  static_assert(OUT % 4 == 0, "layer width must be a multiple of 4");
+#pragma unroll
+  for (int j = 0; j < OUT; j++) o[j] = make_float2(0.0f, 0.0f);
+#pragma unroll
+  for (int k = 0; k < IN; k++) {
+#pragma unroll
+    for (int j4 = 0; j4 < OUT / 4; j4++) {
+      const float4 w = load_w4<WSRC>(sw, const_off, k * (OUT / 4) + j4);
+      o[4 * j4 + 0] = __ffma2_rn(make_float2(w.x, w.x), a[k], o[4 * j4 + 0]);
+      o[4 * j4 + 1] = __ffma2_rn(make_float2(w.y, w.y), a[k], o[4 * j4 + 1]);
+      o[4 * j4 + 2] = __ffma2_rn(make_float2(w.z, w.z), a[k], o[4 * j4 + 2]);
+      o[4 * j4 + 3] = __ffma2_rn(make_float2(w.w, w.w), a[k], o[4 * j4 + 3]);
+    }
+  }
+#pragma unroll
+  for (int j4 = 0; j4 < OUT / 4; j4++) {
+    const float4 b = load_w4<WSRC>(sw + IN * OUT, const_off + IN * OUT, j4);
+    o[4 * j4 + 0] = __fadd2_rn(o[4 * j4 + 0], make_float2(b.x, b.x));
+    o[4 * j4 + 1] = __fadd2_rn(o[4 * j4 + 1], make_float2(b.y, b.y));
+    o[4 * j4 + 2] = __fadd2_rn(o[4 * j4 + 2], make_float2(b.z, b.z));
+    o[4 * j4 + 3] = __fadd2_rn(o[4 * j4 + 3], make_float2(b.w, b.w));
+    if (ACT) {
+      o[4 * j4 + 0] = tanh_fast2(o[4 * j4 + 0]);
+      o[4 * j4 + 1] = tanh_fast2(o[4 * j4 + 1]);
+      o[4 * j4 + 2] = tanh_fast2(o[4 * j4 + 2]);
+      o[4 * j4 + 3] = tanh_fast2(o[4 * j4 + 3]);
+    }
+  }
+}
+
+template <int WSRC, int IN, int OUT, int... Rest>
+struct NetChainP2 {
+  using Shape = NetShape<IN, OUT, Rest...>;
+  static constexpr int LAST = Shape::LAST;
+  __device__ __forceinline__ static void forward(const float *__restrict__ sw, int const_off, const float2 (&a)[IN], float2 (&out)[LAST]) {
+    if constexpr (sizeof...(Rest) == 0) {
+      dense_layer_p2<IN, OUT, false, WSRC>(sw, const_off, a, out);
+    } else {
+      float2 h[OUT];
+      dense_layer_p2<IN, OUT, true, WSRC>(sw, const_off, a, h);
+      NetChainP2<WSRC, OUT, Rest...>::forward(sw + IN * OUT + OUT, const_off + IN * OUT + OUT, h, out);
+    }
+  }
+};
+
+template <int WSRC_, int... W>
+struct NeuralNetDynP2 {
+  static constexpr int R = 2;
+  static constexpr int WSRC = WSRC_;
+  static constexpr int SMEM_FLOATS = WSRC_ == 0 ? NetShape<W...>::NPARAMS : 0;
+  static constexpr int NPARAMS = NetShape<W...>::NPARAMS;
+  __device__ __forceinline__ static void deriv(const float *__restrict__ sw, const float (&in)[6][2], float (&out)[4][2]) {
+    float2 a[6], o[4];
+#pragma unroll
+    for (int k = 0; k < 6; k++) a[k] = make_float2(in[k][0], in[k][1]);
+    NetChainP2<WSRC_, W...>::forward(sw, 0, a, o);
+#pragma unroll
+    for (int k = 0; k < 4; k++) { out[k][0] = o[k].x; out[k][1] = o[k].y; }
+  }
+};
+
 // Dynamics policies consumed by rollout_kernel: deriv() maps [roll, u_x, u_y, yaw_rate, steer,
 // throttle] to d/dt [roll, u_x, u_y, yaw_rate] for R rollouts.
 template <int R_, int... W>

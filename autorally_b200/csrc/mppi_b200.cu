@@ -66,7 +66,11 @@ struct mppi_ctx {
   bool injected = false;
   std::vector<float> injected_noise;
   uint64_t seed = 1234;
-  uint32_t call_counter = 0;
+  uint32_t *d_call_counter = nullptr;
+  // CUDA graph of one complete computeControl (H2D inbox -> kernels -> D2H outbox)
+  cudaGraphExec_t graph_exec = nullptr;
+  bool graph_valid = false;
+  int graph_launches = 0;
   // bookkeeping
   int variant = MPPI_ROLLOUT_THREAD1;
   int launches = 0;
@@ -109,10 +113,12 @@ int resolve_variant(const mppi_ctx *c) {
   if (v == MPPI_ROLLOUT_AUTO) {
     // Latency regime: too few rollouts to give every SM sub-partition a warp with one thread per
     // rollout -> spread each rollout over 8 lanes.  Throughput regime: register-tile 2 rollouts.
-    if (total <= 148 * 512) v = MPPI_ROLLOUT_THREAD1;
+    if (total <= 3072) v = MPPI_ROLLOUT_LANES32;
+    else if (total <= 8192) v = MPPI_ROLLOUT_LANES16;
+    else if (total <= 32768) v = MPPI_ROLLOUT_LANES8;
     else v = MPPI_ROLLOUT_THREAD2;
   }
-  if (v == MPPI_ROLLOUT_CONST1 || v == MPPI_ROLLOUT_SPLIT8) v = MPPI_ROLLOUT_THREAD1;  // not built yet
+  if (v == MPPI_ROLLOUT_CONST1) v = MPPI_ROLLOUT_THREAD2;  // constant-bank weights measured no faster (profiles/microbench_r01.txt)
   return v;
 }
 
@@ -133,6 +139,10 @@ cudaError_t launch_rollout(mppi_ctx *c) {
   if (c->net_kind == 64) return launch_rollout_nn64_r1(p, c->stream, small);
   switch (c->variant) {
     case MPPI_ROLLOUT_THREAD2: return launch_rollout_nn32_r2(p, c->stream, small);
+    case MPPI_ROLLOUT_SPLIT8: return launch_rollout_nn32_split8(p, c->stream);
+    case MPPI_ROLLOUT_LANES8: return launch_rollout_nn32_lanes(p, c->stream, 8);
+    case MPPI_ROLLOUT_LANES16: return launch_rollout_nn32_lanes(p, c->stream, 16);
+    case MPPI_ROLLOUT_LANES32: return launch_rollout_nn32_lanes(p, c->stream, 32);
     default: return launch_rollout_nn32_r1(p, c->stream, small);
   }
 }
@@ -143,8 +153,7 @@ cudaError_t launch_noise(mppi_ctx *c) {
   if (blocks > 148 * 16) blocks = 148 * 16;
   c->launches++;
   sample_noise_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(c->d_du, c->n_local, c->r_begin, c->T, c->B, (uint32_t)c->seed,
-                                                              (uint32_t)(c->seed >> 32), c->call_counter);
-  c->call_counter++;
+                                                              (uint32_t)(c->seed >> 32), c->d_call_counter);
   return cudaGetLastError();
 }
 
@@ -175,6 +184,7 @@ cudaError_t launch_finalize(mppi_ctx *c, const float *gathered, int G, int last_
   p.outbox_stride = c->outbox_stride; p.gamma = c->gamma; p.dt = c->dt;
   p.lo0 = c->ranges[0]; p.hi0 = c->ranges[1]; p.lo1 = c->ranges[2]; p.hi1 = c->ranges[3];
   p.negate_yaw = c->negate_yaw; p.last_iter = last_iter; p.feed_back = feed_back;
+  p.baseline = c->d_baseline; p.call_counter = c->d_call_counter;
   c->launches++;
   finalize_kernel<<<c->B, 256, finalize_smem(c), c->stream>>>(p);
   return cudaGetLastError();
@@ -206,8 +216,7 @@ int run_front(mppi_ctx *c, int iter) {
   } else {
     CK(launch_noise(c));
   }
-  CK(cudaMemsetAsync(c->d_baseline, 0xff, sizeof(unsigned int) * c->B, c->stream));
-  CK(launch_rollout(c));
+  CK(launch_rollout(c));   // the baseline slots were re-armed by the previous finalize_kernel
   CK(launch_weighting(c));
   return MPPI_OK;
 }
@@ -303,6 +312,9 @@ int mppi_create(const mppi_config *cfg, mppi_ctx **out) {
   CKF(cudaMalloc(&c->d_shard, B * c->shard_floats * sizeof(float)));
   CKF(cudaMalloc(&c->d_inv_step, T * sizeof(double)));
   CKF(cudaMalloc(&c->d_net_structure, 16 * sizeof(int)));
+  CKF(cudaMalloc(&c->d_call_counter, sizeof(uint32_t)));
+  CKF(cudaMemset(c->d_call_counter, 0, sizeof(uint32_t)));
+  CKF(cudaMemset(c->d_baseline, 0xff, B * sizeof(unsigned int)));
   CKF(cudaMemset(c->d_done, 0, B * sizeof(unsigned int)));
   CKF(cudaMemset(c->d_inbox, 0, B * c->inbox_stride * sizeof(float)));
   {
@@ -323,6 +335,8 @@ int mppi_destroy(mppi_ctx *c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->map_tex) cudaDestroyTextureObject(c->map_tex);
   if (c->map_array) cudaFreeArray(c->map_array);
+  if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+  cudaFree(c->d_call_counter);
   cudaFree(c->d_theta_t); cudaFree(c->d_net_structure); cudaFree(c->d_inbox); cudaFree(c->d_outbox);
   cudaFreeHost(c->h_inbox); cudaFreeHost(c->h_outbox);
   cudaFree(c->d_du); cudaFree(c->d_costs); cudaFree(c->d_crash); cudaFree(c->d_baseline); cudaFree(c->d_done);
@@ -337,6 +351,7 @@ int mppi_destroy(mppi_ctx *c) {
 }
 
 static int upload_theta(mppi_ctx *c) {
+  c->graph_valid = false;
   CK(cudaSetDevice(c->device));
   CK(cudaStreamSynchronize(c->stream));
   const size_t bytes = round_up((int)c->theta_t.size(), 4) * sizeof(float);
@@ -391,18 +406,21 @@ int mppi_set_bf_params(mppi_ctx *c, const float *theta) {
 
 int mppi_set_control_ranges(mppi_ctx *c, const float lo_hi[4]) {
   if (!c || !lo_hi) return MPPI_ERR_INVALID_ARG;
+  c->graph_valid = false;
   std::memcpy(c->ranges, lo_hi, sizeof(c->ranges));
   return MPPI_OK;
 }
 
 int mppi_set_negate_yaw_der(mppi_ctx *c, int negate) {
   if (!c) return MPPI_ERR_INVALID_ARG;
+  c->graph_valid = false;
   c->negate_yaw = negate ? 1 : 0;
   return MPPI_OK;
 }
 
 int mppi_set_cost_params(mppi_ctx *c, const mppi_cost_params *p) {
   if (!c || !p) return MPPI_ERR_INVALID_ARG;
+  c->graph_valid = false;
   c->cost_params = *p;
   fill_dev_cost_params(c);
   c->have_cost_params = true;
@@ -411,6 +429,7 @@ int mppi_set_cost_params(mppi_ctx *c, const mppi_cost_params *p) {
 
 int mppi_set_costmap(mppi_ctx *c, const float *texels, int width, int height, int channels) {
   if (!c || !texels || width <= 0 || height <= 0 || (channels != 1 && channels != 4)) return MPPI_ERR_INVALID_ARG;
+  c->graph_valid = false;
   CK(cudaSetDevice(c->device));
   CK(cudaStreamSynchronize(c->stream));
   if (c->map_tex) { cudaDestroyTextureObject(c->map_tex); c->map_tex = 0; }
@@ -440,18 +459,21 @@ int mppi_set_costmap(mppi_ctx *c, const float *texels, int width, int height, in
 
 int mppi_set_exploration_std(mppi_ctx *c, const float std2[2]) {
   if (!c || !std2) return MPPI_ERR_INVALID_ARG;
+  c->graph_valid = false;
   c->nu[0] = std2[0]; c->nu[1] = std2[1];
   return MPPI_OK;
 }
 
 int mppi_set_gamma(mppi_ctx *c, float gamma) {
   if (!c) return MPPI_ERR_INVALID_ARG;
+  c->graph_valid = false;
   c->gamma = gamma;
   return MPPI_OK;
 }
 
 int mppi_set_noise(mppi_ctx *c, const float *eps, size_t count) {
   if (!c || !eps) return MPPI_ERR_INVALID_ARG;
+  c->graph_valid = false;
   const size_t per_iter = (size_t)c->B * c->n_local * c->T * 2;
   if (count < per_iter * (size_t)c->cfg.num_iters) return MPPI_ERR_INVALID_ARG;
   c->injected_noise.assign(eps, eps + per_iter * c->cfg.num_iters);
@@ -461,6 +483,7 @@ int mppi_set_noise(mppi_ctx *c, const float *eps, size_t count) {
 
 int mppi_use_sampler(mppi_ctx *c) {
   if (!c) return MPPI_ERR_INVALID_ARG;
+  c->graph_valid = false;
   c->injected = false;
   c->injected_noise.clear();
   c->injected_noise.shrink_to_fit();
@@ -469,7 +492,11 @@ int mppi_use_sampler(mppi_ctx *c) {
 
 int mppi_seed(mppi_ctx *c, uint64_t seed, uint32_t call_counter) {
   if (!c) return MPPI_ERR_INVALID_ARG;
-  c->seed = seed; c->call_counter = call_counter;
+  c->seed = seed;
+  c->graph_valid = false;
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaMemcpy(c->d_call_counter, &call_counter, sizeof(uint32_t), cudaMemcpyHostToDevice));
   return MPPI_OK;
 }
 
@@ -478,8 +505,20 @@ int mppi_sample_noise(mppi_ctx *c, float *eps_out) {
   CK(cudaSetDevice(c->device));
   c->launches = 0;
   CK(launch_noise(c));
+  bump_counter_kernel<<<1, 1, 0, c->stream>>>(c->d_call_counter);
   if (eps_out) CK(cudaMemcpyAsync(eps_out, c->d_du, (size_t)c->B * c->n_local * c->T * 2 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  return MPPI_OK;
+}
+
+static int enqueue_compute(mppi_ctx *c) {
+  CK(cudaMemcpyAsync(c->d_inbox, c->h_inbox, (size_t)c->B * c->inbox_stride * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  for (int it = 0; it < c->cfg.num_iters; it++) {
+    int rc = run_front(c, it);
+    if (rc) return rc;
+    CK(launch_finalize(c, c->d_shard, 1, it == c->cfg.num_iters - 1, 0));
+  }
+  CK(cudaMemcpyAsync(c->h_outbox, c->d_outbox, (size_t)c->B * c->outbox_stride * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   return MPPI_OK;
 }
 
@@ -488,16 +527,33 @@ int mppi_compute_control(mppi_ctx *c, const float *state, float *U, const float 
   if (rc) return rc;
   if (!state || !U) return MPPI_ERR_INVALID_ARG;
   CK(cudaSetDevice(c->device));
-  c->launches = 0;
   stage_inbox(c, state, U, hist);
-  CK(cudaMemcpyAsync(c->d_inbox, c->h_inbox, (size_t)c->B * c->inbox_stride * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   c->have_inbox = true;
-  for (int it = 0; it < c->cfg.num_iters; it++) {
-    rc = run_front(c, it);
+  if (c->injected) {  // parity path: noise comes from pageable host memory, plain stream launches
+    c->launches = 0;
+    rc = enqueue_compute(c);
     if (rc) return rc;
-    CK(launch_finalize(c, c->d_shard, 1, it == c->cfg.num_iters - 1, 0));
+  } else {
+    // The whole call (H2D of state/U/history, sampler, rollouts, weighting, finalize, D2H of the
+    // results) is one CUDA graph; it is re-captured only when a setter changed a baked-in parameter.
+    if (!c->graph_valid) {
+      if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+      cudaGraph_t graph = nullptr;
+      c->launches = 0;
+      CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+      rc = enqueue_compute(c);
+      cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+      if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+      CK(ce);
+      ce = cudaGraphInstantiate(&c->graph_exec, graph, 0);
+      cudaGraphDestroy(graph);
+      CK(ce);
+      c->graph_launches = c->launches;
+      c->graph_valid = true;
+    }
+    c->launches = c->graph_launches;
+    CK(cudaGraphLaunch(c->graph_exec, c->stream));
   }
-  CK(cudaMemcpyAsync(c->h_outbox, c->d_outbox, (size_t)c->B * c->outbox_stride * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   unpack_outbox(c, U, ss, cs, res);
   return MPPI_OK;
@@ -593,7 +649,6 @@ int mppi_run_resident(mppi_ctx *c, int steps, int flush_l2, float *elapsed_ms, f
     if (per_step) CK(cudaEventRecord(c->step_events[4 * s], c->stream));
     for (int it = 0; it < c->cfg.num_iters; it++) {
       CK(launch_noise(c));
-      CK(cudaMemsetAsync(c->d_baseline, 0xff, sizeof(unsigned int) * c->B, c->stream));
       if (per_step && it == 0) CK(cudaEventRecord(c->step_events[4 * s + 2], c->stream));
       CK(launch_rollout(c));
       if (per_step && it == 0) CK(cudaEventRecord(c->step_events[4 * s + 3], c->stream));

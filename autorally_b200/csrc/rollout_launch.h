@@ -8,10 +8,9 @@ namespace mppi {
 // `small` selects 32-thread CTAs so that a few thousand rollouts still spread over many SMs.
 cudaError_t launch_rollout_nn32_r1(const RolloutParams &p, cudaStream_t st, bool small);
 cudaError_t launch_rollout_nn32_r2(const RolloutParams &p, cudaStream_t st, bool small);
+cudaError_t launch_rollout_nn32_split8(const RolloutParams &p, cudaStream_t st);
+cudaError_t launch_rollout_nn32_lanes(const RolloutParams &p, cudaStream_t st, int lanes);
 cudaError_t launch_rollout_nn64_r1(const RolloutParams &p, cudaStream_t st, bool small);
 cudaError_t launch_rollout_bf(const RolloutParams &p, cudaStream_t st, bool small);
-
-template <class DYN, int BLOCK>
-struct RolloutLauncher;
 
 }  // namespace mppi

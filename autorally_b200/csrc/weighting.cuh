@@ -37,8 +37,12 @@ __device__ __forceinline__ float2 box_muller(uint32_t xa, uint32_t xb) {
   return make_float2(rad * cs, rad * sn);
 }
 
+// `call_ptr` is the device-resident compute-call counter (advanced by finalize_kernel), so a captured
+// CUDA graph replays with a fresh Philox offset every launch.
 __global__ void __launch_bounds__(256) sample_noise_kernel(float *__restrict__ du, int n_local, int r_begin, int T,
-                                                            int B, uint32_t seed_lo, uint32_t seed_hi, uint32_t call) {
+                                                            int B, uint32_t seed_lo, uint32_t seed_hi,
+                                                            const uint32_t *__restrict__ call_ptr) {
+  const uint32_t call = *call_ptr;
   const int Q = (T + 1) >> 1;
   const long long total = (long long)B * n_local * Q;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -187,6 +191,8 @@ struct FinalizeParams {
   int negate_yaw;
   int last_iter;          // 1: smooth + nominal trajectory; 0: U <- U_new only (num_iters > 1)
   int feed_back;          // 1: write the smoothed U back into the inbox (resident stepping)
+  unsigned int *baseline; // [B] re-armed (0xffffffff) for the next rollout launch
+  uint32_t *call_counter; // advanced once per launch (Philox offset of the next sampler launch)
 };
 
 constexpr int FIN_MAX_WIDTH = 128;
@@ -199,9 +205,86 @@ __device__ __forceinline__ void car_basis_host_twin(const float *theta, const fl
   for (int j = 0; j < 4; j++) out4[j] = o[j][0];
 }
 
+// Nominal trajectory for the 6-32-32-4 network on ONE warp (computeNominalTraj, PI/mppi_controller.cu:501-519).
+// Lane j owns hidden neuron j of both hidden layers with its weights in registers; activations cross
+// lanes through shared memory; layer 2 uses 4 interleaved partial sums (8 FMAs deep instead of 32) and
+// layer 3 is (4 outputs) x (8 chunks) with a xor tree, so one step is a ~300-cycle dependent chain.
+// x / y need sincosf(yaw) only for the OUTPUT, so they are filled in 32 steps at a time by all lanes in
+// parallel (sequential FMA prefix, the reference's Euler order).  Within the 1e-4 parity tolerance of
+// the host twin (FMA contraction and tanh_fast differ from Eigen/libm in the last bits).
+__device__ __forceinline__ void nominal_traj_nn32(const float *__restrict__ sw, const float *__restrict__ inbox,
+                                                  const float *__restrict__ Usm, int T, float dt, int negate_yaw, float lo0,
+                                                  float hi0, float lo1, float hi1, float *__restrict__ ssol,
+                                                  float *__restrict__ csol, float *__restrict__ act, int lane) {
+  constexpr int kW1 = 0, kB1 = 192, kW2 = 224, kB2 = 1248, kW3 = 1280, kB3 = 1408;
+  const unsigned full = 0xffffffffu;
+  float w1[6], w2[32], w3[4];
+#pragma unroll
+  for (int k = 0; k < 6; k++) w1[k] = sw[kW1 + k * 32 + lane];
+#pragma unroll
+  for (int k = 0; k < 32; k++) w2[k] = sw[kW2 + k * 32 + lane];
+  const int jo = lane & 3, chunk = lane >> 2;
+#pragma unroll
+  for (int kk = 0; kk < 4; kk++) w3[kk] = sw[kW3 + (chunk * 4 + kk) * 4 + jo];
+  const float b1 = sw[kB1 + lane], b2 = sw[kB2 + lane], b3 = sw[kB3 + jo];
+  float x = inbox[INBOX_STATE + 0], y = inbox[INBOX_STATE + 1], yaw = inbox[INBOX_STATE + 2];
+  float roll = inbox[INBOX_STATE + 3], vx = inbox[INBOX_STATE + 4], vy = inbox[INBOX_STATE + 5], wz = inbox[INBOX_STATE + 6];
+  float *h1 = act, *h2 = act + 64;
+  for (int i0 = 0; i0 < T; i0 += 32) {
+    const int nb = min(32, T - i0);
+    float r_yaw = 0.0f, r_roll = 0.0f, r_vx = 0.0f, r_vy = 0.0f, r_wz = 0.0f;
+    for (int ii = 0; ii < nb; ii++) {
+      const int i = i0 + ii;
+      float u0 = Usm[2 * i], u1 = Usm[2 * i + 1];
+      u0 = u0 < lo0 ? lo0 : (u0 > hi0 ? hi0 : u0);
+      u1 = u1 < lo1 ? lo1 : (u1 > hi1 ? hi1 : u1);
+      if (lane == ii) { r_yaw = yaw; r_roll = roll; r_vx = vx; r_vy = vy; r_wz = wz; csol[2 * i] = u0; csol[2 * i + 1] = u1; }
+      float t = w1[0] * roll;
+      t = fmaf(w1[1], vx, t); t = fmaf(w1[2], vy, t); t = fmaf(w1[3], wz, t); t = fmaf(w1[4], u0, t); t = fmaf(w1[5], u1, t);
+      float *hb = h1 + (i & 1) * 32;
+      hb[lane] = tanh_fast(t + b1);
+      __syncwarp();
+      float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+#pragma unroll
+      for (int k4 = 0; k4 < 8; k4++) {
+        const float4 hv = reinterpret_cast<const float4 *>(hb)[k4];
+        a0 = fmaf(w2[4 * k4 + 0], hv.x, a0); a1 = fmaf(w2[4 * k4 + 1], hv.y, a1);
+        a2 = fmaf(w2[4 * k4 + 2], hv.z, a2); a3 = fmaf(w2[4 * k4 + 3], hv.w, a3);
+      }
+      float *gb = h2 + (i & 1) * 32;
+      gb[lane] = tanh_fast(((a0 + a1) + (a2 + a3)) + b2);
+      __syncwarp();
+      const float4 gv = reinterpret_cast<const float4 *>(gb)[chunk];
+      float part = w3[0] * gv.x;
+      part = fmaf(w3[1], gv.y, part); part = fmaf(w3[2], gv.z, part); part = fmaf(w3[3], gv.w, part);
+      part += __shfl_xor_sync(full, part, 4); part += __shfl_xor_sync(full, part, 8); part += __shfl_xor_sync(full, part, 16);
+      part += b3;
+      const float o0 = __shfl_sync(full, part, 0), o1 = __shfl_sync(full, part, 1);
+      const float o2 = __shfl_sync(full, part, 2), o3 = __shfl_sync(full, part, 3);
+      yaw = fmaf(negate_yaw ? -wz : wz, dt, yaw);
+      roll = fmaf(o0, dt, roll); vx = fmaf(o1, dt, vx); vy = fmaf(o2, dt, vy); wz = fmaf(o3, dt, wz);
+    }
+    float sn, cs;
+    sincosf(r_yaw, &sn, &cs);
+    const float d0 = fmaf(cs, r_vx, -__fmul_rn(sn, r_vy)), d1 = fmaf(sn, r_vx, __fmul_rn(cs, r_vy));
+    float myx = 0.0f, myy = 0.0f;
+    for (int j = 0; j < nb; j++) {
+      if (lane == j) { myx = x; myy = y; }
+      x = fmaf(__shfl_sync(full, d0, j), dt, x);
+      y = fmaf(__shfl_sync(full, d1, j), dt, y);
+    }
+    if (lane < nb) {
+      float *o = ssol + (size_t)(i0 + lane) * S_DIM;
+      o[0] = myx; o[1] = myy; o[2] = r_yaw; o[3] = r_roll; o[4] = r_vx; o[5] = r_vy; o[6] = r_wz;
+    }
+  }
+}
+
 // grid B, block 256.  Combines the G shard records (log-sum-exp rescale),
 // U_new = W / Z (control update :663-667), Savitzky-Golay (:468-499), then warp 0 integrates the
 // nominal trajectory with the host-twin arithmetic (separate multiply and add, precise tanhf/sinf/cosf).
+__global__ void bump_counter_kernel(uint32_t *counter) { *counter += 1u; }
+
 __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ FinalizeParams p) {
   extern __shared__ float fsm[];
   const int T = p.T, tid = threadIdx.x, b = blockIdx.x;
@@ -235,6 +318,10 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ F
     Unew[k] = wsum / Z;
   }
   if (tid < 4) outbox[tid] = hdr[tid];
+  if (tid == 0) {
+    p.baseline[b] = 0xffffffffu;
+    if (b == 0) *p.call_counter += 1u;
+  }
   __syncthreads();
   for (int k = tid; k < 2 * T; k += 256) outbox[4 + 2 * T + k] = Unew[k];
   if (!p.last_iter) {
@@ -272,10 +359,14 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ F
   if (tid >= 32) return;
   // ---- nominal trajectory (computeNominalTraj :501-519 -> host updateState) on warp 0 ----
   const int lane = tid;
-  float s[S_DIM];
-  for (int k = 0; k < S_DIM; k++) s[k] = inbox[INBOX_STATE + k];
   float *ssol = outbox + 4 + 4 * T;
   float *csol = ssol + S_DIM * T;
+  if (p.num_layers == 4 && p.net_structure[0] == 6 && p.net_structure[1] == 32 && p.net_structure[2] == 32 && p.net_structure[3] == 4) {
+    nominal_traj_nn32(sw, inbox, Usm, T, p.dt, p.negate_yaw, p.lo0, p.hi0, p.lo1, p.hi1, ssol, csol, act, lane);
+    return;
+  }
+  float s[S_DIM];
+  for (int k = 0; k < S_DIM; k++) s[k] = inbox[INBOX_STATE + k];
   for (int i = 0; i < T; i++) {
     if (lane == 0) {
 #pragma unroll

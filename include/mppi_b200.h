@@ -47,8 +47,11 @@ enum {
   MPPI_ROLLOUT_AUTO = 0,
   MPPI_ROLLOUT_THREAD1 = 1, /* one rollout per thread, weights broadcast from shared memory */
   MPPI_ROLLOUT_THREAD2 = 2, /* two rollouts per thread (register-tiled), weights from shared memory */
-  MPPI_ROLLOUT_SPLIT8 = 3,  /* one rollout across 8 lanes (latency configuration) */
-  MPPI_ROLLOUT_CONST1 = 4   /* one rollout per thread, weights as constant-bank operands */
+  MPPI_ROLLOUT_SPLIT8 = 3,  /* one rollout across 8 lanes, costs replicated in the lanes */
+  MPPI_ROLLOUT_CONST1 = 4,  /* reserved: weights as constant-bank operands (measured no faster) */
+  MPPI_ROLLOUT_LANES8 = 5,  /* one rollout across 8 / 16 / 32 lanes, cost evaluation deferred and */
+  MPPI_ROLLOUT_LANES16 = 6, /* spread over the lanes: the latency configurations (1920 rollouts -> 32) */
+  MPPI_ROLLOUT_LANES32 = 7
 };
 
 /* Replaces the MPPIController template/ctor arguments (PI/mppi_controller.cuh:52-53,101-102) plus the

@@ -101,6 +101,27 @@ __global__ void __launch_bounds__(128) k_layer_const(float *out, int iters) {
   if (s == 123.456f) out[0] = s;
 }
 
+template <int WSRC, bool ACT>
+__global__ void __launch_bounds__(128) k_layer_p2(float *out, const float *w, int iters) {
+  __shared__ float4 sw4[(32 * 32 + 32) / 4];
+  for (int i = threadIdx.x; i < (32 * 32 + 32) / 4; i += 128) sw4[i] = reinterpret_cast<const float4 *>(w)[i];
+  __syncthreads();
+  const float *sw = reinterpret_cast<const float *>(sw4);
+  float2 a[32], o[32];
+#pragma unroll
+  for (int k = 0; k < 32; k++) a[k] = make_float2(0.001f * (threadIdx.x + k), 0.002f * (threadIdx.x + k));
+  for (int it = 0; it < iters; it++) {
+    asm volatile("" ::: "memory");
+    dense_layer_p2<32, 32, ACT, WSRC>(sw, 0, a, o);
+#pragma unroll
+    for (int k = 0; k < 32; k++) a[k] = o[k];
+  }
+  float2 s = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < 32; k++) s = __fadd2_rn(s, a[k]);
+  if (s.x == 123.456f) out[0] = s.y;
+}
+
 __global__ void __launch_bounds__(256) k_tanh(float *out, float a, int iters) {
   float x[8];
 #pragma unroll
@@ -174,6 +195,18 @@ int main() {
       printf("layer32x32 const R=1 (%d CTA/SM of 128): %7.2f TFLOP/s\n", bps, fl * 1 * 128.0 * nb / ms / 1e9);
       ms = time_ms([&] { k_layer_const<2><<<nb, 128>>>(d, it); });
       printf("layer32x32 const R=2 (%d CTA/SM of 128): %7.2f TFLOP/s\n", bps, fl * 2 * 128.0 * nb / ms / 1e9);
+    }
+    cudaMemcpyToSymbol(c_theta, hw, sizeof(hw));
+    for (int bps = 3; bps <= 6; bps += 3) {
+      const int nbp = sms * bps;
+      float msp = time_ms([&] { k_layer_p2<0, false><<<nbp, 128>>>(d, w, it); });
+      printf("layer32x32 FFMA2 smem  (%d CTA/SM of 128): %7.2f TFLOP/s\n", bps, fl * 2 * 128.0 * nbp / msp / 1e9);
+      msp = time_ms([&] { k_layer_p2<1, false><<<nbp, 128>>>(d, w, it); });
+      printf("layer32x32 FFMA2 const (%d CTA/SM of 128): %7.2f TFLOP/s\n", bps, fl * 2 * 128.0 * nbp / msp / 1e9);
+      msp = time_ms([&] { k_layer_p2<0, true><<<nbp, 128>>>(d, w, it); });
+      printf("layer32x32 FFMA2 smem +tanh2 (%d CTA/SM): %7.2f TFLOP/s (FMA flops only)\n", bps, fl * 2 * 128.0 * nbp / msp / 1e9);
+      msp = time_ms([&] { k_layer_p2<1, true><<<nbp, 128>>>(d, w, it); });
+      printf("layer32x32 FFMA2 const+tanh2 (%d CTA/SM): %7.2f TFLOP/s (FMA flops only)\n", bps, fl * 2 * 128.0 * nbp / msp / 1e9);
     }
     const int nb = sms * 4;
     float ms = time_ms([&] { k_layer_smem<4, false><<<nb, 128>>>(d, w, it); });
