@@ -406,6 +406,7 @@ int mppi_set_bf_params(mppi_ctx *c, const float *theta) {
 
 int mppi_set_control_ranges(mppi_ctx *c, const float lo_hi[4]) {
   if (!c || !lo_hi) return MPPI_ERR_INVALID_ARG;
+  if (!std::memcmp(c->ranges, lo_hi, sizeof(c->ranges))) return MPPI_OK;  // unchanged: keep the captured graph
   c->graph_valid = false;
   std::memcpy(c->ranges, lo_hi, sizeof(c->ranges));
   return MPPI_OK;
@@ -413,6 +414,7 @@ int mppi_set_control_ranges(mppi_ctx *c, const float lo_hi[4]) {
 
 int mppi_set_negate_yaw_der(mppi_ctx *c, int negate) {
   if (!c) return MPPI_ERR_INVALID_ARG;
+  if (c->negate_yaw == (negate ? 1 : 0)) return MPPI_OK;
   c->graph_valid = false;
   c->negate_yaw = negate ? 1 : 0;
   return MPPI_OK;
@@ -420,6 +422,7 @@ int mppi_set_negate_yaw_der(mppi_ctx *c, int negate) {
 
 int mppi_set_cost_params(mppi_ctx *c, const mppi_cost_params *p) {
   if (!c || !p) return MPPI_ERR_INVALID_ARG;
+  if (c->have_cost_params && !std::memcmp(&c->cost_params, p, sizeof(*p))) return MPPI_OK;
   c->graph_valid = false;
   c->cost_params = *p;
   fill_dev_cost_params(c);
@@ -459,6 +462,7 @@ int mppi_set_costmap(mppi_ctx *c, const float *texels, int width, int height, in
 
 int mppi_set_exploration_std(mppi_ctx *c, const float std2[2]) {
   if (!c || !std2) return MPPI_ERR_INVALID_ARG;
+  if (c->nu[0] == std2[0] && c->nu[1] == std2[1]) return MPPI_OK;
   c->graph_valid = false;
   c->nu[0] = std2[0]; c->nu[1] = std2[1];
   return MPPI_OK;
@@ -466,6 +470,7 @@ int mppi_set_exploration_std(mppi_ctx *c, const float std2[2]) {
 
 int mppi_set_gamma(mppi_ctx *c, float gamma) {
   if (!c) return MPPI_ERR_INVALID_ARG;
+  if (c->gamma == gamma) return MPPI_OK;
   c->graph_valid = false;
   c->gamma = gamma;
   return MPPI_OK;
