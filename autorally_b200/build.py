@@ -56,7 +56,7 @@ def build_library(force=False, verbose=False):
             print(out)
         if p.returncode != 0:
             raise RuntimeError("nvcc failed: %s\n%s" % (" ".join(cmd), out))
-    link = [_nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    link = [_nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
     subprocess.check_call(link)
     return LIB
 

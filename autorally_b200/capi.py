@@ -34,6 +34,9 @@ EXPORTED_SYMBOLS = [
     "mppi_get_unsmoothed_controls", "mppi_shard_floats", "mppi_shard_begin", "mppi_shard_partials_device",
     "mppi_shard_finish", "mppi_run_resident", "mppi_get_stream", "mppi_synchronize",
     "mppi_last_launch_count", "mppi_resolved_variant", "mppi_measure_fp32_peak", "mppi_measure_copy_bandwidth",
+    "mppi_shard_begin_async", "mppi_shard_finish_async", "mppi_shard_result", "mppi_set_stream",
+    "mppi_comm_unique_id", "mppi_comm_init", "mppi_comm_destroy", "mppi_compute_control_sharded",
+    "mppi_run_resident_sharded",
 ]
 
 
@@ -74,6 +77,8 @@ def load_library():
         lib.mppi_seed.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32]
         lib.mppi_measure_copy_bandwidth.argtypes = [ctypes.c_int, ctypes.c_size_t, c_float_p]
         lib.mppi_set_gamma.argtypes = [ctypes.c_void_p, ctypes.c_float]
+        lib.mppi_set_stream.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        lib.mppi_comm_init.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int]
         _lib = lib
     return _lib
 
@@ -245,6 +250,66 @@ class MppiContext:
         if B == 1:
             out = {k: v[0] for k, v in out.items()}
         return out
+
+    def _result(self, U, ss, cs, res):
+        out = dict(U=U, state_solution=ss, control_solution=cs,
+                   baseline=np.array([r.baseline for r in res], np.float32),
+                   normalizer=np.array([r.normalizer for r in res], np.float32),
+                   trajectory_cost=np.array([r.trajectory_cost for r in res], np.float32))
+        return {k: v[0] for k, v in out.items()} if self.B == 1 else out
+
+    def set_stream(self, cuda_stream):
+        """Enqueue on the caller's stream (an int handle, e.g. torch.cuda.current_stream().cuda_stream)."""
+        self._ck(self.lib.mppi_set_stream(self._ctx, ctypes.c_void_p(cuda_stream)), "mppi_set_stream")
+
+    def shard_begin_async(self, state=None, U=None, hist=None):
+        B, T = self.B, self.T
+        if state is None:
+            self._ck(self.lib.mppi_shard_begin_async(self._ctx, None, None, None), "mppi_shard_begin_async")
+            return
+        state, U = _f32(state).reshape(B, 7), _f32(U).reshape(B, T, 2)
+        hist = _f32(hist if hist is not None else np.zeros((B, 4))).reshape(B, 4)
+        self._ck(self.lib.mppi_shard_begin_async(self._ctx, _fp(state), _fp(U), _fp(hist)), "mppi_shard_begin_async")
+
+    def shard_finish_async(self, gathered_dev_ptr, num_shards, feed_back=False):
+        self._ck(self.lib.mppi_shard_finish_async(self._ctx, ctypes.cast(ctypes.c_void_p(gathered_dev_ptr), c_float_p), int(num_shards),
+                                                  int(bool(feed_back))), "mppi_shard_finish_async")
+
+    def shard_result(self):
+        B, T = self.B, self.T
+        U, ss, cs = np.zeros((B, T, 2), np.float32), np.zeros((B, T, 7), np.float32), np.zeros((B, T, 2), np.float32)
+        res = (MppiResult * B)()
+        self._ck(self.lib.mppi_shard_result(self._ctx, _fp(U), _fp(ss), _fp(cs), res), "mppi_shard_result")
+        return self._result(U, ss, cs, res)
+
+    # ---- in-library NCCL exchange ----------------------------------------------------
+    @staticmethod
+    def comm_unique_id():
+        buf = ctypes.create_string_buffer(128)
+        code = load_library().mppi_comm_unique_id(buf)
+        if code:
+            raise MppiError(code, "mppi_comm_unique_id")
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, rank: int, num_ranks: int):
+        assert len(unique_id) == 128
+        self._ck(self.lib.mppi_comm_init(self._ctx, unique_id, int(rank), int(num_ranks)), "mppi_comm_init")
+
+    def compute_control_sharded(self, state, U, hist=None):
+        B, T = self.B, self.T
+        state = _f32(state).reshape(B, 7)
+        U = _f32(U).reshape(B, T, 2).copy()
+        hist = _f32(hist if hist is not None else np.zeros((B, 4))).reshape(B, 4)
+        ss, cs = np.zeros((B, T, 7), np.float32), np.zeros((B, T, 2), np.float32)
+        res = (MppiResult * B)()
+        self._ck(self.lib.mppi_compute_control_sharded(self._ctx, _fp(state), _fp(U), _fp(hist), _fp(ss), _fp(cs), res),
+                 "mppi_compute_control_sharded")
+        return self._result(U, ss, cs, res)
+
+    def run_resident_sharded(self, steps):
+        el = ctypes.c_float(0)
+        self._ck(self.lib.mppi_run_resident_sharded(self._ctx, int(steps), ctypes.byref(el)), "mppi_run_resident_sharded")
+        return el.value
 
     # ---- measurement -----------------------------------------------------------------
     def run_resident(self, steps, time_rollout=False, flush_l2=False):

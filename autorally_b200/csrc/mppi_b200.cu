@@ -3,6 +3,7 @@
 #include "../../include/mppi_b200.h"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <cmath>
 #include <cstdio>
@@ -34,6 +35,11 @@ struct mppi_ctx {
   int device = 0;
   int n_local = 0, r_begin = 0, B = 1, T = 0;
   cudaStream_t stream = nullptr;
+  bool owns_stream = true;
+  // NCCL exchange (mppi_comm_init): communicator and the gathered records [num_ranks][B][shard_floats]
+  void *nccl_comm = nullptr;
+  int comm_rank = 0, comm_size = 1;
+  float *d_gathered = nullptr;
   // model
   bool have_model = false, have_cost_params = false, have_map = false, have_inbox = false;
   int net_kind = 0;  // 0 none, 32 = 6-32-32-4, 64 = 6-64-64-64-64-4
@@ -247,6 +253,7 @@ const char *mppi_error_string(int code) {
     case MPPI_ERR_NOT_READY: return "model, cost parameters or costmap not set";
     case MPPI_ERR_NO_DEVICE: return "no CUDA device (there is no CPU fallback)";
     case MPPI_ERR_ALLOC: return "allocation failed";
+    case MPPI_ERR_COMM: return "NCCL unavailable or an NCCL call failed";
     default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
   }
 }
@@ -332,7 +339,8 @@ int mppi_create(const mppi_config *cfg, mppi_ctx **out) {
 int mppi_destroy(mppi_ctx *c) {
   if (!c) return MPPI_OK;
   cudaSetDevice(c->device);
-  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->stream || !c->owns_stream) cudaStreamSynchronize(c->stream);
+  mppi_comm_destroy(c);
   if (c->map_tex) cudaDestroyTextureObject(c->map_tex);
   if (c->map_array) cudaFreeArray(c->map_array);
   if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
@@ -344,7 +352,7 @@ int mppi_destroy(mppi_ctx *c) {
   for (cudaEvent_t e : c->step_events) cudaEventDestroy(e);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
-  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->stream && c->owns_stream) cudaStreamDestroy(c->stream);
   cudaGetLastError();
   delete c;
   return MPPI_OK;
@@ -599,17 +607,26 @@ int mppi_get_unsmoothed_controls(mppi_ctx *c, float *U_new) {
 
 int mppi_shard_floats(const mppi_ctx *c) { return c ? c->shard_floats : MPPI_ERR_INVALID_ARG; }
 
-int mppi_shard_begin(mppi_ctx *c, const float *state, const float *U, const float *hist) {
+int mppi_shard_begin_async(mppi_ctx *c, const float *state, const float *U, const float *hist) {
   int rc = check_ready(c);
   if (rc) return rc;
-  if (!state || !U) return MPPI_ERR_INVALID_ARG;
   if (c->cfg.num_iters != 1) return MPPI_ERR_UNSUPPORTED;  // one exchange per computeControl
   CK(cudaSetDevice(c->device));
   c->launches = 0;
-  stage_inbox(c, state, U, hist);
-  CK(cudaMemcpyAsync(c->d_inbox, c->h_inbox, (size_t)c->B * c->inbox_stride * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-  c->have_inbox = true;
-  rc = run_front(c, 0);
+  if (state) {
+    if (!U) return MPPI_ERR_INVALID_ARG;
+    stage_inbox(c, state, U, hist);
+    CK(cudaMemcpyAsync(c->d_inbox, c->h_inbox, (size_t)c->B * c->inbox_stride * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    c->have_inbox = true;
+  } else if (!c->have_inbox) {
+    return MPPI_ERR_INVALID_ARG;
+  }
+  return run_front(c, 0);
+}
+
+int mppi_shard_begin(mppi_ctx *c, const float *state, const float *U, const float *hist) {
+  if (!state || !U) return MPPI_ERR_INVALID_ARG;
+  int rc = mppi_shard_begin_async(c, state, U, hist);
   if (rc) return rc;
   CK(cudaStreamSynchronize(c->stream));  // the exchange runs on the caller's (NCCL) stream
   return MPPI_OK;
@@ -621,15 +638,155 @@ int mppi_shard_partials_device(mppi_ctx *c, float **dev_ptr) {
   return MPPI_OK;
 }
 
-int mppi_shard_finish(mppi_ctx *c, const float *gathered_dev, int num_shards, float *U, float *ss, float *cs, mppi_result *res) {
+int mppi_shard_finish_async(mppi_ctx *c, const float *gathered_dev, int num_shards, int feed_back) {
   int rc = check_ready(c);
   if (rc) return rc;
   if (!gathered_dev || num_shards < 1 || num_shards > 64) return MPPI_ERR_INVALID_ARG;
   CK(cudaSetDevice(c->device));
-  CK(launch_finalize(c, gathered_dev, num_shards, 1, 0));
+  CK(launch_finalize(c, gathered_dev, num_shards, 1, feed_back ? 1 : 0));
+  CK(cudaMemcpyAsync(c->h_outbox, c->d_outbox, (size_t)c->B * c->outbox_stride * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  return MPPI_OK;
+}
+
+int mppi_shard_result(mppi_ctx *c, float *U, float *ss, float *cs, mppi_result *res) {
+  if (!c) return MPPI_ERR_INVALID_ARG;
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  unpack_outbox(c, U, ss, cs, res);
+  return MPPI_OK;
+}
+
+int mppi_shard_finish(mppi_ctx *c, const float *gathered_dev, int num_shards, float *U, float *ss, float *cs, mppi_result *res) {
+  int rc = mppi_shard_finish_async(c, gathered_dev, num_shards, 0);
+  if (rc) return rc;
+  return mppi_shard_result(c, U, ss, cs, res);
+}
+
+int mppi_set_stream(mppi_ctx *c, void *cuda_stream) {
+  if (!c) return MPPI_ERR_INVALID_ARG;
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  if (c->owns_stream && c->stream) cudaStreamDestroy(c->stream);
+  c->stream = (cudaStream_t)cuda_stream;
+  c->owns_stream = false;
+  c->graph_valid = false;
+  return MPPI_OK;
+}
+
+// ---------------------------------------------------------------- NCCL exchange (dlopen) ----
+namespace {
+struct NcclUniqueId { char internal[128]; };  // ncclUniqueId, nccl.h: NCCL_UNIQUE_ID_BYTES = 128
+struct NcclApi {
+  void *handle = nullptr;
+  int (*GetUniqueId)(NcclUniqueId *) = nullptr;
+  int (*CommInitRank)(void **, int, NcclUniqueId, int) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void *) = nullptr;
+  bool ok = false;
+};
+NcclApi &nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    // under torchrun the process already holds torch's bundled libnccl.so.2: dlopen by soname returns that copy
+    api.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!api.handle) api.handle = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (api.handle) {
+      api.GetUniqueId = (int (*)(NcclUniqueId *))dlsym(api.handle, "ncclGetUniqueId");
+      api.CommInitRank = (int (*)(void **, int, NcclUniqueId, int))dlsym(api.handle, "ncclCommInitRank");
+      api.AllGather = (int (*)(const void *, void *, size_t, int, void *, cudaStream_t))dlsym(api.handle, "ncclAllGather");
+      api.CommDestroy = (int (*)(void *))dlsym(api.handle, "ncclCommDestroy");
+      api.ok = api.GetUniqueId && api.CommInitRank && api.AllGather && api.CommDestroy;
+    }
+  }
+  return api;
+}
+constexpr int kNcclFloat = 7;  // ncclFloat32 (nccl.h: ncclDataType_t)
+
+// front -> all-gather of the shard records -> finalize, all on the context's stream
+int enqueue_sharded(mppi_ctx *c, int feed_back) {
+  int rc = run_front(c, 0);
+  if (rc) return rc;
+  const size_t count = (size_t)c->B * c->shard_floats;
+  if (nccl_api().AllGather(c->d_shard, c->d_gathered, count, kNcclFloat, c->nccl_comm, c->stream) != 0) return MPPI_ERR_COMM;
+  CK(launch_finalize(c, c->d_gathered, c->comm_size, 1, feed_back));
+  return MPPI_OK;
+}
+}  // namespace
+
+int mppi_comm_unique_id(void *id_out) {
+  if (!id_out) return MPPI_ERR_INVALID_ARG;
+  NcclApi &api = nccl_api();
+  if (!api.ok) return MPPI_ERR_COMM;
+  NcclUniqueId id;
+  if (api.GetUniqueId(&id) != 0) return MPPI_ERR_COMM;
+  std::memcpy(id_out, &id, sizeof(id));
+  return MPPI_OK;
+}
+
+int mppi_comm_init(mppi_ctx *c, const void *id_bytes, int rank, int num_ranks) {
+  if (!c || !id_bytes || num_ranks < 1 || num_ranks > 64 || rank < 0 || rank >= num_ranks) return MPPI_ERR_INVALID_ARG;
+  NcclApi &api = nccl_api();
+  if (!api.ok) return MPPI_ERR_COMM;
+  CK(cudaSetDevice(c->device));
+  mppi_comm_destroy(c);
+  NcclUniqueId id;
+  std::memcpy(&id, id_bytes, sizeof(id));
+  if (api.CommInitRank(&c->nccl_comm, num_ranks, id, rank) != 0) { c->nccl_comm = nullptr; return MPPI_ERR_COMM; }
+  c->comm_rank = rank; c->comm_size = num_ranks;
+  CK(cudaMalloc(&c->d_gathered, (size_t)num_ranks * c->B * c->shard_floats * sizeof(float)));
+  c->graph_valid = false;
+  return MPPI_OK;
+}
+
+int mppi_comm_destroy(mppi_ctx *c) {
+  if (!c) return MPPI_ERR_INVALID_ARG;
+  if (c->nccl_comm) {
+    cudaStreamSynchronize(c->stream);
+    nccl_api().CommDestroy(c->nccl_comm);
+    c->nccl_comm = nullptr;
+  }
+  if (c->d_gathered) { cudaFree(c->d_gathered); c->d_gathered = nullptr; }
+  c->comm_size = 1; c->comm_rank = 0;
+  return MPPI_OK;
+}
+
+int mppi_compute_control_sharded(mppi_ctx *c, const float *state, float *U, const float *hist, float *ss, float *cs, mppi_result *res) {
+  int rc = check_ready(c);
+  if (rc) return rc;
+  if (!state || !U) return MPPI_ERR_INVALID_ARG;
+  if (!c->nccl_comm) return MPPI_ERR_NOT_READY;
+  if (c->cfg.num_iters != 1) return MPPI_ERR_UNSUPPORTED;
+  CK(cudaSetDevice(c->device));
+  stage_inbox(c, state, U, hist);
+  c->have_inbox = true;
+  c->launches = 0;
+  CK(cudaMemcpyAsync(c->d_inbox, c->h_inbox, (size_t)c->B * c->inbox_stride * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  rc = enqueue_sharded(c, 0);
+  if (rc) return rc;
   CK(cudaMemcpyAsync(c->h_outbox, c->d_outbox, (size_t)c->B * c->outbox_stride * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   unpack_outbox(c, U, ss, cs, res);
+  return MPPI_OK;
+}
+
+int mppi_run_resident_sharded(mppi_ctx *c, int steps, float *elapsed_ms) {
+  int rc = check_ready(c);
+  if (rc) return rc;
+  if (steps < 1 || !c->have_inbox || c->injected || !c->nccl_comm) return MPPI_ERR_INVALID_ARG;
+  CK(cudaSetDevice(c->device));
+  c->launches = 0;
+  CK(cudaEventRecord(c->ev0, c->stream));
+  for (int s = 0; s < steps; s++) {
+    rc = enqueue_sharded(c, 1);
+    if (rc) return rc;
+  }
+  CK(cudaEventRecord(c->ev1, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  float ms = 0.0f;
+  CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  if (elapsed_ms) *elapsed_ms = ms;
   return MPPI_OK;
 }
 

@@ -33,13 +33,22 @@ N_ROLLOUTS, T_STEPS = 1920, 100
 LARGE_ROLLOUTS = 1 << 20           # "large-sample MPPI": 1M rollouts (16384 x 64)
 
 
+WORKLOAD = "path_integral_nn: NeuralNetModel<7,2,3,6,32,32,4>, 1920 rollouts x 100 steps, synthetic ellipse costmap"
+
+
+def bench_config(world):
+    return {"workload": WORKLOAD, "rollouts": N_ROLLOUTS, "timesteps": T_STEPS,
+            "parallelism": "one controller per GPU x%d (independent controllers, no communication)" % world}
+
+
 def load_setup():
     from autorally_b200.params import make_ellipse_costmap
-    from tests.common import cost_params_for, default_state, warm_controls
+    from tests.common import cost_params_for, straight_controls, top_state
     models = np.load(os.path.join(ROOT, "tests", "golden", "ref_models.npz"))
     costmap = make_ellipse_costmap()
     cp = cost_params_for(costmap)
-    return models, costmap, cp, default_state(5.0), warm_controls(T_STEPS)
+    # flat top of the ellipse at 4 m/s: ~30% of the rollouts survive, importance weights spread over many rollouts
+    return models, costmap, cp, top_state(4.0), straight_controls(T_STEPS)
 
 
 class ClockSampler:
@@ -151,31 +160,66 @@ def cpu_baseline(models, costmap, cp, state, U, budget_s=12.0):
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path (oracle port; the reference's C++/CUDA cannot be built
-    here) on the box's host cores; under torchrun only rank 0 works."""
+    """--impl reference.  The reference implements computeControl only in CUDA (there is no CPU path), so when
+    oracle/_ref/libautorally_ref.so (the reference's own sources built by oracle/refbuild.py) and a GPU are present this
+    arm runs the UNMODIFIED reference controller -- its kernels, cuRAND noise, host syncs and copies -- through its public
+    computeControl(state) on the same B200.  Otherwise it times the CPU port (oracle/mppi_oracle.c) on all host cores.
+    Under torchrun only rank 0 works; the other ranks exit 0."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     models, costmap, cp, state, U = load_setup()
-    from tests.common import make_oracle
-    o = make_oracle("nn", models, costmap, cp)
     cores = os.cpu_count() or 1
-    rng = np.random.default_rng(0)
-    eps = rng.standard_normal((1, N_ROLLOUTS, T_STEPS, 2)).astype(np.float32)
-    Uc = U.copy()
-    for _ in range(args.warmup):
-        Uc = o.compute_control(state, Uc, np.zeros(4), [0.275, 0.3], eps, threads=cores)["U"]
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        Uc = o.compute_control(state, Uc, np.zeros(4), [0.275, 0.3], eps, threads=cores)["U"]
-    dt = time.perf_counter() - t0
-    val = N_ROLLOUTS * T_STEPS * args.steps / dt
-    line = {"impl": "reference", "metric": "rollout-steps/sec", "value": val, "unit": "rollout-steps/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "path_integral_nn 1920 rollouts x 100 steps, ellipse costmap (CPU, host cores)"},
-            "cpu_baseline": {"value": val, "unit": "rollout-steps/s", "cores": cores, "kind": "port",
-                             "sample": "%d x full computeControl on %d pthreads" % (args.steps, cores)},
-            "e2e": {"value": val, "unit": "rollout-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    line = {"impl": "reference", "metric": "rollout-steps/sec", "unit": "rollout-steps/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic"}
+    gpu_ok = False
+    try:
+        import torch
+        from oracle import reference as ref
+        gpu_ok = ref.available() and torch.cuda.is_available()
+    except Exception:
+        gpu_ok = False
+    if gpu_ok:
+        with ref.ReferenceController(ref.REF_NN_1920, models["autorally_nnet_theta"], costmap, cp) as rc:
+            rc.set_controls(U, np.zeros(4, np.float32))
+            for _ in range(max(args.warmup, 1)):
+                rc.compute_control(state, want_eps=False)
+            lat = []
+            t_all = time.perf_counter()
+            for _ in range(args.steps):
+                t0 = time.perf_counter()
+                rc.compute_control(state, want_eps=False)
+                lat.append(time.perf_counter() - t0)
+            dt = time.perf_counter() - t_all
+        lat.sort()
+        val = N_ROLLOUTS * T_STEPS * args.steps / dt
+        line.update(value=val, ms_per_step=1e3 * dt / args.steps,
+                    config=bench_config(1),
+                    reference_impl="rdesc/autorally MPPIController<NeuralNetModel<7,2,3,6,32,32,4>,MPPICosts,1920,8,16>::computeControl, "
+                                   "its own CUDA kernels and cuRAND noise, sources compiled unmodified for sm_100a (oracle/refbuild.py), "
+                                   "on this B200",
+                    p50_ms=1e3 * lat[len(lat) // 2],
+                    cpu_baseline={"value": val, "unit": "rollout-steps/s", "cores": 1, "kind": "reference",
+                                  "sample": "%d x reference computeControl(1920x100) from oracle/_ref (GPU kernels + 1 host thread; "
+                                            "the reference has no CPU implementation of this path)" % args.steps},
+                    e2e={"value": val, "unit": "rollout-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+    else:
+        from tests.common import make_oracle
+        o = make_oracle("nn", models, costmap, cp)
+        eps = np.random.default_rng(0).standard_normal((1, N_ROLLOUTS, T_STEPS, 2)).astype(np.float32)
+        Uc = U.copy()
+        for _ in range(args.warmup):
+            Uc = o.compute_control(state, Uc, np.zeros(4), [0.275, 0.3], eps, threads=cores)["U"]
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            Uc = o.compute_control(state, Uc, np.zeros(4), [0.275, 0.3], eps, threads=cores)["U"]
+        dt = time.perf_counter() - t0
+        val = N_ROLLOUTS * T_STEPS * args.steps / dt
+        line.update(value=val, ms_per_step=1e3 * dt / args.steps, config=bench_config(1),
+                    reference_impl="CPU port of the reference (oracle/mppi_oracle.c) on all host cores: oracle/_ref or a GPU is missing",
+                    cpu_baseline={"value": val, "unit": "rollout-steps/s", "cores": cores, "kind": "port",
+                                  "sample": "%d x full computeControl, oracle/mppi_oracle.c on %d pthreads" % (args.steps, cores)},
+                    e2e={"value": val, "unit": "rollout-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
     print(json.dumps(line))
 
 
@@ -273,18 +317,25 @@ def main():
            "h2d_bytes_per_step": int(4 * (12 + 2 * T_STEPS)), "d2h_bytes_per_step": int(4 * (4 + 13 * T_STEPS)),
            "p50_ms": 1e3 * lat[len(lat) // 2], "p99_ms": 1e3 * lat[min(len(lat) - 1, int(0.99 * len(lat)))]}
     rollout_ms = rk / args.steps
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")
+    if os.path.exists(tpath):   # dram__bytes_read.sum + dram__bytes_write.sum of the rollout kernel, one ncu --set full capture
+        t = json.load(open(tpath))["configs"]
+        k = t["1920"]["rollout_lanes_kernel"]
+        traffic, traffic_src = k["dram_read_bytes"] + k["dram_write_bytes"], "profiles/ncu_traffic_r01.json (cold-cache ncu replay)"
     achieved = FLOP_PER_ROLLOUT_STEP_NN * N_ROLLOUTS * T_STEPS / (rollout_ms * 1e-3) / 1e12
     roofline = {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-                "traffic": None, "kernel": "rollout_kernel", "kernel_ms": rollout_ms,
+                "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": 16.0 * N_ROLLOUTS * T_STEPS,
+                "kernel": "rollout_lanes_kernel<32>" if ctx.resolved_variant() == 7 else "rollout kernel (variant %d)" % ctx.resolved_variant(),
+                "kernel_ms": rollout_ms,
                 "note": "FP32 FFMA issue bound (CUDA cores; neither HBM nor tensor); peak = FFMA microbenchmark measured in this run; "
                         "1920 rollouts occupy <2% of the machine, see 'large' for the filled-GPU fraction"}
     line = {"metric": "rollout-steps/sec", "value": value, "unit": "rollout-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "path_integral_nn: NeuralNetModel<7,2,3,6,32,32,4>, 1920 rollouts x 100 steps, ellipse costmap, "
-                                   "one controller per GPU", "rollouts": N_ROLLOUTS, "timesteps": T_STEPS,
-                       "l2": "flushed between timed steps (256 MiB memset outside the timed intervals)",
-                       "variant": ctx.resolved_variant(), "parallelism": "independent controllers x%d" % world},
+            "config": bench_config(world), "rollout_variant": ctx.resolved_variant(),
+            "l2": "flushed between timed steps (256 MiB memset outside the timed intervals)",
+            "per_gpu": value / world,
             "ms_per_step_warm_l2": ms_warm / args.steps, "e2e": e2e, "gpu_launches": launches + e2e_launches,
             "roofline": roofline, "clocks": clk.summary(), "fp32_peak_tflops_measured": fp32_peak,
             "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src,
@@ -304,38 +355,30 @@ def main():
 
 
 def run_sharded_large(models, costmap, cp, state, U, world, rank, local_rank, barrier, max_over_ranks, steps=5):
-    """configs[3]: 1M rollouts x 100 steps sharded over the ranks; one NCCL all-gather of the
-    3+2T-float partial record per step."""
-    import torch
+    """configs[3]: 1M rollouts x 100 steps sharded over the ranks; per step ONE ncclAllGather of the (4 + 2T)-float
+    shard record per rank, issued by the library on the context's stream between the weighting
+    and finalize kernels.  Device-resident, timed with CUDA events on that stream, max over ranks."""
     import torch.distributed as dist
+    from autorally_b200.capi import MppiContext
+    from autorally_b200.sharding import rollout_shard
     from tests.common import make_context
-    from tests.test_parity_gpu import ctypes_float_array
-    chunks = LARGE_ROLLOUTS // 64
-    lo, hi = chunks * rank // world * 64, chunks * (rank + 1) // world * 64
-    ctx = make_context("nn", models, costmap, cp, LARGE_ROLLOUTS, rollout_begin=lo, rollout_count=hi - lo, device=local_rank)
+    lo, n = rollout_shard(rank, world, LARGE_ROLLOUTS)
+    ids = [MppiContext.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    ctx = make_context("nn", models, costmap, cp, LARGE_ROLLOUTS, rollout_begin=lo, rollout_count=n, device=local_rank)
+    ctx.comm_init(ids[0], rank, world)
+    out = ctx.compute_control_sharded(state, U)      # initialises the device-resident state / U
+    ctx.run_resident_sharded(2)
+    barrier()
+    ms = ctx.run_resident_sharded(steps)
+    barrier()
+    ms = max_over_ranks(ms)
     sf = ctx.shard_floats()
-    mine = ctypes_float_array(ctx.shard_partials_ptr(), sf)
-    gathered = torch.empty((world, sf), dtype=torch.float32, device="cuda")
-    Uc = U.copy()
-
-    def step(Uc):
-        ctx.shard_begin(state, Uc)
-        dist.all_gather_into_tensor(gathered.view(-1), mine)
-        torch.cuda.current_stream().synchronize()
-        return ctx.shard_finish(gathered.data_ptr(), world)["U"]
-    for _ in range(2):
-        Uc = step(Uc)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        Uc = step(Uc)
-    barrier()
-    dt = max_over_ranks(time.perf_counter() - t0)
     ctx.close()
-    return {"rollouts": LARGE_ROLLOUTS, "steps": steps, "ms_per_step": 1e3 * dt / steps,
-            "value": LARGE_ROLLOUTS * T_STEPS * steps / dt, "unit": "rollout-steps/s",
-            "exchange": "all_gather of %d floats per rank per step (NCCL)" % sf, "timing": "host wall clock incl. H2D/D2H, max over ranks"}
+    return {"rollouts": LARGE_ROLLOUTS, "rollouts_per_gpu": n, "steps": steps, "ms_per_step": ms / steps,
+            "value": LARGE_ROLLOUTS * T_STEPS * steps / (ms * 1e-3), "unit": "rollout-steps/s", "scaling": "strong",
+            "exchange": "one ncclAllGather of %d floats per rank per step, inside the library, on the compute stream" % sf,
+            "timing": "CUDA events on the context's stream, max over ranks", "normalizer": float(out["normalizer"])}
 
 
 if __name__ == "__main__":

@@ -37,7 +37,8 @@ enum {
   MPPI_ERR_UNSUPPORTED = -2,   /* e.g. an MLP structure no kernel is instantiated for */
   MPPI_ERR_NOT_READY = -3,     /* compute called before weights / costmap / cost params were set */
   MPPI_ERR_NO_DEVICE = -4,     /* no CUDA device: there is no CPU fallback */
-  MPPI_ERR_ALLOC = -5
+  MPPI_ERR_ALLOC = -5,
+  MPPI_ERR_COMM = -6           /* libnccl.so.2 not loadable, or an NCCL call failed */
 };
 
 enum { MPPI_DYNAMICS_NN = 0, MPPI_DYNAMICS_BF = 1 };
@@ -153,6 +154,29 @@ int mppi_shard_begin(mppi_ctx *ctx, const float *state, const float *U, const fl
 int mppi_shard_partials_device(mppi_ctx *ctx, float **dev_ptr);
 int mppi_shard_finish(mppi_ctx *ctx, const float *gathered_dev, int num_shards, float *U,
                       float *state_solution, float *control_solution, mppi_result *result);
+
+/* Asynchronous halves of the two calls above, for callers that order the exchange on a stream instead of the host
+ * (bench.py, the in-library NCCL path).  mppi_shard_begin_async with state == NULL reuses the device-resident
+ * state / U / history (the smoothed U of the previous mppi_shard_finish_async with feed_back != 0).  Nothing
+ * synchronises until mppi_shard_result, which waits for the stream and unpacks the last finish. */
+int mppi_shard_begin_async(mppi_ctx *ctx, const float *state, const float *U, const float *control_hist);
+int mppi_shard_finish_async(mppi_ctx *ctx, const float *gathered_dev, int num_shards, int feed_back);
+int mppi_shard_result(mppi_ctx *ctx, float *U, float *state_solution, float *control_solution, mppi_result *result);
+/* Run on the caller's stream (e.g. the one its NCCL calls are ordered on) instead of the context's own. */
+int mppi_set_stream(mppi_ctx *ctx, void *cuda_stream);
+
+/* In-library exchange over NCCL (libnccl.so.2 is loaded at run time with dlopen; the library has no link-time
+ * dependency on it).  One process per GPU: rank 0 calls mppi_comm_unique_id, ships the 128 bytes to the other
+ * ranks out of band, and every rank calls mppi_comm_init.  mppi_compute_control_sharded is then computeControl
+ * for this rank's shard of the rollouts: sampler -> rollouts -> local weighting record -> ONE ncclAllGather of
+ * mppi_shard_floats() floats per controller -> finalize, all on the context's stream; every rank returns the same U. */
+int mppi_comm_unique_id(void *id_out_128_bytes);
+int mppi_comm_init(mppi_ctx *ctx, const void *id_128_bytes, int rank, int num_ranks);
+int mppi_comm_destroy(mppi_ctx *ctx);
+int mppi_compute_control_sharded(mppi_ctx *ctx, const float *state, float *U, const float *control_hist,
+                                 float *state_solution, float *control_solution, mppi_result *result);
+/* Device-resident sharded stepping (throughput measurement): `steps` sharded pipelines back to back, no host copies. */
+int mppi_run_resident_sharded(mppi_ctx *ctx, int steps, float *elapsed_ms);
 
 /* Device-resident stepping for throughput measurement: runs `steps` complete pipelines back to back
  * with state/U/history already in HBM and no host copies (the smoothed U of one step warm-starts the

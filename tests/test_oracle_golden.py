@@ -142,3 +142,48 @@ def test_bf_oracle_runs_and_is_finite(models, small_costmap):
     eps = np.random.default_rng(6).standard_normal((128, 40, 2)).astype(np.float32)
     V, costs, crash, fs = o.rollouts(default_state(), warm_controls(40), [0.275, 0.3], eps)
     assert np.all(np.isfinite(costs)) and np.all(np.isfinite(fs))
+
+
+# ---- pinned against the reference's own kernels (tests/golden/make_ref_gpu_golden.py, run on a B200) --------------
+def _ref_gpu_cases():
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_gpu_golden.npz")
+    if not os.path.exists(path):
+        return None, []
+    z = np.load(path)
+    return z, sorted({k.split("/")[0] for k in z.files})
+
+
+_REF_GPU, _REF_GPU_CASES = _ref_gpu_cases()
+
+
+@pytest.mark.skipif(not _REF_GPU_CASES, reason="tests/golden/ref_gpu_golden.npz not generated yet")
+@pytest.mark.parametrize("case", _REF_GPU_CASES)
+def test_oracle_matches_reference_gpu_outputs(models, costmap, case):
+    """The CPU oracle against outputs of the REFERENCE's own MPPIController (rolloutKernel, normExpKernel,
+    weightedReductionKernel, device dynamics and costs, host smoothing and nominal rollout) recorded on a B200 with the
+    noise its cuRAND generator drew.  This is what makes the oracle "pinned": bookkeeping bit-exact, costs within
+    1e-4 relative for >= 99% of the rollouts (the rest are discrete threshold flips), controls within 1e-4."""
+    from tests.common import cost_params_for, make_oracle
+    z = _REF_GPU
+    g = lambda k: z[case + "/" + k]
+    T, opt_delay, is_bf = (int(v) for v in g("cfg"))
+    sc, tc, slop, l1, slip, vdes = (float(v) for v in g("cost_over"))
+    cp = cost_params_for(costmap, steering_coeff=sc, throttle_coeff=tc, track_slop=slop, l1_cost=bool(l1), max_slip_ang=slip,
+                         desired_speed=vdes)
+    o = make_oracle("bf" if is_bf else "nn", models, costmap, cp)
+    got = o.compute_control(g("state"), g("U_in"), g("hist"), [0.275, 0.3], g("eps"), opt_delay=opt_delay, threads=4)
+    np.testing.assert_array_equal(got["V"][0], g("V_row0"))    # noise-free rollout 0 (PI/mppi_controller.cu:136-140)
+    np.testing.assert_array_equal(got["V"][-1], g("V_last"))   # pure-noise tail (:141-145)
+    want_c = g("costs")
+    err = np.abs(got["costs"] - want_c) / (1 + np.abs(want_c))
+    tol = 2e-4 if is_bf else 1e-4
+    assert (err < tol).mean() >= 0.99, "only %.2f%% of costs within %g" % (100 * (err < tol).mean(), tol)
+    assert abs(got["costs"].min() - want_c.min()) <= tol * (1 + abs(want_c.min()))
+    np.testing.assert_allclose(got["w"], g("w"), rtol=5e-3, atol=1e-6)
+    normalizer, traj_cost = g("scalars")
+    assert abs(got["normalizer"] - normalizer) <= 1e-3 * normalizer
+    assert abs(got["trajectory_cost"] - traj_cost) <= 1e-3 * traj_cost
+    for k in ("U", "state_solution", "control_solution"):
+        e = np.abs(got[k] - g(k)) / (1 + np.abs(g(k)))
+        assert e.max() < 1e-4, "%s: max rel err %.3g" % (k, e.max())

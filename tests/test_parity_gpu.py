@@ -12,7 +12,7 @@ whole discrete quanta, and hold the baseline and the weighted controls to the fu
 import numpy as np
 import pytest
 
-from tests.common import cost_params_for, default_state, make_context, make_oracle, warm_controls
+from tests.common import cost_params_for, default_state, make_context, make_oracle, straight_controls, top_state, warm_controls
 
 pytestmark = pytest.mark.gpu
 
@@ -24,18 +24,18 @@ def rel_err(a, b, floor=1.0):
 
 
 def run_pair(kind, models, costmap, N, T=100, speed=5.0, seed=11, variant=0, cp_over=None, tag="autorally_nnet",
-             negate=True, opt_delay=1):
+             negate=True, opt_delay=1, scenario="tip", gamma=0.15):
     cp = cost_params_for(costmap, **(cp_over or {}))
     if kind == "bf":
         cp.desired_speed = 6.0
     eps = np.random.default_rng(seed).standard_normal((1, N, T, 2)).astype(np.float32)
-    U = warm_controls(T)
+    U = warm_controls(T) if scenario == "tip" else straight_controls(T)
     hist = np.array([0.1, 0.3, 0.11, 0.32], np.float32)
-    state = default_state(speed)
+    state = default_state(speed) if scenario == "tip" else top_state(speed)
     o = make_oracle(kind, models, costmap, cp, tag=tag, negate_yaw_der=negate)
-    want = o.compute_control(state, U, hist, NU, eps, opt_delay=opt_delay, threads=8)
+    want = o.compute_control(state, U, hist, NU, eps, gamma=gamma, opt_delay=opt_delay, threads=8)
     with make_context(kind, models, costmap, cp, N, tag=tag, negate_yaw_der=negate, num_timesteps=T, variant=variant,
-                      optimization_stride=opt_delay) as ctx:
+                      optimization_stride=opt_delay, gamma=gamma) as ctx:
         ctx.set_noise(eps)
         got = ctx.compute_control(state, U, hist)
         got["costs"] = ctx.rollout_costs()
@@ -82,6 +82,22 @@ def test_nn_1920x100_matches_oracle(models, costmap, variant, speed):
     """BASELINE config 2: path_integral_nn, 1920 rollouts x 100 steps, synthetic ellipse costmap."""
     want, got = run_pair("nn", models, costmap, 1920, speed=speed, variant=variant)
     check_pair(want, got)
+
+
+@pytest.mark.parametrize("variant", [1, 2, 5, 7])
+@pytest.mark.parametrize("gamma", [0.15, 0.01])
+def test_nn_spread_weights_match_oracle(models, costmap, variant, gamma):
+    """Flat top of the ellipse at 4 m/s: ~30% of the rollouts survive and the weights are spread over many
+    rollouts (normaliser ~30 at gamma 0.15, ~400 at 0.01), so the weighted control reduction is really exercised --
+    at the tip of the ellipse every rollout crashes and the weights collapse onto the single best one."""
+    want, got = run_pair("nn", models, costmap, 1920, speed=4.0, variant=variant, scenario="top", gamma=gamma)
+    assert want["normalizer"] > (20 if gamma > 0.1 else 200)
+    check_pair(want, got)
+
+
+def test_bf_spread_weights_match_oracle(models, costmap):
+    want, got = run_pair("bf", models, costmap, 2560, speed=4.0, scenario="top")
+    check_pair(want, got, cost_tol=2e-4)
 
 
 def test_bf_2560x100_matches_oracle(models, costmap):

@@ -1,0 +1,162 @@
+"""GPU: three-way parity -- the REFERENCE's own MPPIController (oracle/_ref/libautorally_ref.so, built from
+/root/reference by oracle/refbuild.py and run here on the B200), the CUDA product path (through the C ABI)
+and the CPU oracle, all on the SAME noise: the N(0,1) draws the reference's cuRAND generator produced.
+
+This is what pins the oracle: rdesc/autorally ships no tests or golden vectors for this path, so its own
+kernels, compiled unmodified and executed on the GPU box, are the authority.  Tolerances as in
+tests/test_parity_gpu.py: bookkeeping bit-exact; costs / controls within 1e-4 relative, with <= 1% of the
+rollouts allowed to differ by discrete events (crash / slip-kill flips at a threshold).
+"""
+import numpy as np
+import pytest
+
+from oracle import reference as ref
+from tests.common import cost_params_for, default_state, make_context, make_oracle, straight_controls, top_state, warm_controls
+from tests.test_parity_gpu import check_costs, rel_err
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libautorally_ref.so not built")]
+
+NU = np.array([0.275, 0.3], np.float32)
+HIST = np.array([0.1, 0.3, 0.11, 0.32], np.float32)
+
+
+def reference_run(kind, theta, costmap, cp, state, U, T=100, init_u=(0.0, 0.0), opt_delay=1, iters=1, gamma=0.15):
+    with ref.ReferenceController(kind, theta, costmap, cp, num_timesteps=T, init_u=init_u, optimization_stride=opt_delay,
+                                 num_iters=iters, gamma=gamma) as rc:
+        rc.set_controls(U, HIST)
+        out = rc.compute_control(state)
+        out["costs"], out["V"] = rc.rollout_costs(state, U, out["eps"][0])
+    return out
+
+
+def compare(got, want, T, what, cost_tol=1e-4, u_tol=1e-4):
+    np.testing.assert_array_equal(got["V"], want["V"], err_msg=what + ": sampled-control bookkeeping")
+    check_costs(got["costs"], want["costs"], T, cost_tol)
+    assert abs(got["costs"].min() - want["costs"].min()) <= cost_tol * (1 + abs(want["costs"].min())), what
+    assert rel_err(got["normalizer"], want["normalizer"]) < 1e-3, what
+    assert rel_err(got["trajectory_cost"], want["trajectory_cost"]) < 1e-3, what
+    e = rel_err(got["U"], want["U"]).max()
+    assert e < u_tol, "%s: max control rel err %.3g" % (what, e)
+    assert rel_err(got["state_solution"], want["state_solution"]).max() < 1e-4, what
+    assert rel_err(got["control_solution"], want["control_solution"]).max() < u_tol, what
+
+
+def cuda_run(kind, models, costmap, cp, N, state, U, eps, T=100, opt_delay=1, iters=1, gamma=0.15, variant=0):
+    with make_context(kind, models, costmap, cp, N, num_timesteps=T, optimization_stride=opt_delay, num_iters=iters,
+                      gamma=gamma, variant=variant) as ctx:
+        ctx.set_noise(eps)
+        got = ctx.compute_control(state, U, HIST)
+        if iters == 1:
+            got["costs"], got["V"] = ctx.rollout_costs(), ctx.sampled_controls()
+    return got
+
+
+@pytest.mark.parametrize("speed", [0.0, 5.0, 8.0])
+def test_nn_1920x100_three_way(models, costmap, speed):
+    """BASELINE config 2 against MPPIController<NeuralNetModel<7,2,3,6,32,32,4>, MPPICosts, 1920, 8, 16>."""
+    cp = cost_params_for(costmap)
+    state, U = default_state(speed), warm_controls(100)
+    want = reference_run(ref.REF_NN_1920, models["autorally_nnet_theta"], costmap, cp, state, U)
+    # the twin cuRAND generator really produced the reference's draws: V = U + eps * nu for ordinary rollouts
+    r = 7
+    np.testing.assert_array_equal(want["V"][r, 1:], (U[1:] + want["eps"][0, r, 1:] * NU).astype(np.float32))
+    np.testing.assert_allclose(want["w"], np.exp(-0.15 * (want["costs"] - want["costs"].min())), rtol=2e-5, atol=1e-30)
+    got = cuda_run("nn", models, costmap, cp, 1920, state, U, want["eps"])
+    compare(got, want, 100, "cuda vs reference")
+    o = make_oracle("nn", models, costmap, cp).compute_control(state, U, HIST, NU, want["eps"], threads=8)
+    compare(o, want, 100, "oracle vs reference")
+
+
+@pytest.mark.parametrize("gamma", [0.15, 0.01])
+def test_nn_spread_weights_three_way(models, costmap, gamma):
+    """Flat top of the ellipse at 4 m/s: weights spread over many rollouts (see tests/common.py:top_state)."""
+    cp = cost_params_for(costmap)
+    state, U = top_state(4.0), straight_controls(100)
+    want = reference_run(ref.REF_NN_1920, models["autorally_nnet_theta"], costmap, cp, state, U, gamma=gamma)
+    assert want["normalizer"] > (15 if gamma > 0.1 else 150)
+    for variant in (2, 7):
+        got = cuda_run("nn", models, costmap, cp, 1920, state, U, want["eps"], gamma=gamma, variant=variant)
+        compare(got, want, 100, "cuda (variant %d) vs reference" % variant)
+    o = make_oracle("nn", models, costmap, cp).compute_control(state, U, HIST, NU, want["eps"], gamma=gamma, threads=8)
+    compare(o, want, 100, "oracle vs reference")
+
+
+def test_bf_spread_weights_three_way(models, costmap):
+    cp = cost_params_for(costmap, desired_speed=6.0)
+    state, U = top_state(4.0), straight_controls(100)
+    want = reference_run(ref.REF_BF_2560, models["basis_function_W"], costmap, cp, state, U, init_u=(0.0, -0.01))
+    got = cuda_run("bf", models, costmap, cp, 2560, state, U, want["eps"])
+    compare(got, want, 100, "cuda vs reference", cost_tol=2e-4)
+    o = make_oracle("bf", models, costmap, cp).compute_control(state, U, HIST, NU, want["eps"], threads=8)
+    compare(o, want, 100, "oracle vs reference", cost_tol=2e-4)
+
+
+def test_bf_2560x100_three_way(models, costmap):
+    """BASELINE config 3 against MPPIController<GeneralizedLinear<CarBasisFuncs,7,2,25,CarKinematics,3>, MPPICosts, 2560, 16, 4>.
+    The reference sums the 25 basis-function products with shared-memory atomicAdd (PI/generalized_linear.cu:242-244),
+    so its own result is order-dependent at the 1e-7 level; tolerance 2e-4 as in test_parity_gpu."""
+    cp = cost_params_for(costmap, desired_speed=6.0)
+    state, U = default_state(5.0), warm_controls(100)
+    want = reference_run(ref.REF_BF_2560, models["basis_function_W"], costmap, cp, state, U, init_u=(0.0, -0.01))
+    got = cuda_run("bf", models, costmap, cp, 2560, state, U, want["eps"])
+    compare(got, want, 100, "cuda vs reference", cost_tol=2e-4)
+    o = make_oracle("bf", models, costmap, cp).compute_control(state, U, HIST, NU, want["eps"], threads=8)
+    compare(o, want, 100, "oracle vs reference", cost_tol=2e-4)
+
+
+def test_cost_terms_and_opt_delay_three_way(models, costmap):
+    over = dict(steering_coeff=0.4, throttle_coeff=0.2, track_slop=0.05, l1_cost=True, max_slip_ang=0.4)
+    cp = cost_params_for(costmap, **over)
+    state, U = default_state(6.0), warm_controls(60)
+    want = reference_run(ref.REF_NN_256, models["autorally_nnet_theta"], costmap, cp, state, U, T=60, opt_delay=3)
+    got = cuda_run("nn", models, costmap, cp, 256, state, U, want["eps"], T=60, opt_delay=3)
+    compare(got, want, 60, "cuda vs reference")
+    o = make_oracle("nn", models, costmap, cp).compute_control(state, U, HIST, NU, want["eps"], opt_delay=3, threads=8)
+    compare(o, want, 60, "oracle vs reference")
+
+
+def test_multiple_iterations_three_way(models, costmap):
+    cp = cost_params_for(costmap)
+    state, U = default_state(5.0), warm_controls(100)
+    want = reference_run(ref.REF_NN_4096, models["autorally_nnet_theta"], costmap, cp, state, U, iters=2)
+    got = cuda_run("nn", models, costmap, cp, 4096, state, U, want["eps"], iters=2)
+    assert rel_err(got["U"], want["U"]).max() < 2e-4
+    assert rel_err(got["state_solution"], want["state_solution"]).max() < 2e-4
+    o = make_oracle("nn", models, costmap, cp).compute_control(state, U, HIST, NU, want["eps"], threads=8)
+    assert rel_err(o["U"], want["U"]).max() < 2e-4
+
+
+def test_closed_loop_with_slides_tracks_the_reference(models, costmap):
+    """Five control-loop iterations (slideControlAndStateSeq(1) + computeControl, PI/run_control_loop.cuh:212-219):
+    the CUDA path is fed the reference's U / history / noise each iteration and must reproduce its output; the host
+    sliding logic is checked against the reference's own slideControlSeq."""
+    from oracle.oracle import Oracle
+    cp = cost_params_for(costmap)
+    state = default_state(5.0)
+    o = make_oracle("nn", models, costmap, cp)
+    with ref.ReferenceController(ref.REF_NN_1920, models["autorally_nnet_theta"], costmap, cp) as rc, \
+            make_context("nn", models, costmap, cp, 1920) as ctx:
+        rc.set_controls(warm_controls(100), HIST)
+        for it in range(5):
+            U_in, hist_in = rc.get_controls()
+            want = rc.compute_control(state)
+            ctx.set_noise(want["eps"])
+            got = ctx.compute_control(state, U_in, hist_in)
+            assert rel_err(got["U"], want["U"]).max() < 1e-4, "iteration %d" % it
+            assert rel_err(got["state_solution"], want["state_solution"]).max() < 1e-4
+            U_sl, hist_sl = Oracle.slide_control_seq(want["U"], hist_in, (0.0, 0.0), 1)
+            rc.slide(1)
+            U_ref, hist_ref = rc.get_controls()
+            np.testing.assert_array_equal(U_sl, U_ref)
+            np.testing.assert_array_equal(hist_sl, hist_ref)
+            state, _ = o.update_state(state, want["control_solution"][0])  # plant = host model, as in debug mode
+
+
+def test_reference_latency_is_reported(models, costmap):
+    """The reference's own computeControl wall time on this GPU (printed; bench.py reports it beside ours)."""
+    cp = cost_params_for(costmap)
+    with ref.ReferenceController(ref.REF_NN_1920, models["autorally_nnet_theta"], costmap, cp) as rc:
+        rc.set_controls(warm_controls(100), HIST)
+        ms = rc.time_compute_control(default_state(5.0), reps=10)
+    print("reference computeControl (1920x100, sm_100a build): %.3f ms/call" % ms)
+    assert ms > 0
