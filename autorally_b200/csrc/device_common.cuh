@@ -16,6 +16,8 @@ struct DevCostParams {
   float steering_coeff, throttle_coeff, boundary_threshold;
   float crash_cost_on;  // (float)((1.0 - (double)discount) * (double)crash_coeff), PI/costs.cu:402
   int l1_cost;
+  int has_control_cost;  // steering_coeff != 0 || throttle_coeff != 0
+  int affine;            // r_c1.z == 0 && r_c2.z == 0 && trs.z == 1: the projective divide is the identity
   float c1x, c1y, c1z, c2x, c2y, c2z, tx, ty, tz;  // r_c1, r_c2, trs
 };
 

@@ -98,6 +98,8 @@ void fill_dev_cost_params(mppi_ctx *c) {
   d.boundary_threshold = p.boundary_threshold;
   d.crash_cost_on = (float)((1.0 - (double)p.discount) * (double)p.crash_coeff);  // PI/costs.cu:402
   d.l1_cost = p.l1_cost;
+  d.has_control_cost = (p.steering_coeff != 0.0f || p.throttle_coeff != 0.0f) ? 1 : 0;
+  d.affine = (p.r_c1[2] == 0.0f && p.r_c2[2] == 0.0f && p.trs[2] == 1.0f) ? 1 : 0;
   d.c1x = p.r_c1[0]; d.c1y = p.r_c1[1]; d.c1z = p.r_c1[2];
   d.c2x = p.r_c2[0]; d.c2y = p.r_c2[1]; d.c2z = p.r_c2[2];
   d.tx = p.trs[0]; d.ty = p.trs[1]; d.tz = p.trs[2];
@@ -117,11 +119,9 @@ int resolve_variant(const mppi_ctx *c) {
   if (c->cfg.dynamics == MPPI_DYNAMICS_BF) return MPPI_ROLLOUT_THREAD1;
   if (c->net_kind == 64) return MPPI_ROLLOUT_THREAD1;
   if (v == MPPI_ROLLOUT_AUTO) {
-    // Latency regime: too few rollouts to give every SM sub-partition a warp with one thread per
-    // rollout -> spread each rollout over 8 lanes.  Throughput regime: register-tile 2 rollouts.
-    if (total <= 3072) v = MPPI_ROLLOUT_LANES32;
-    else if (total <= 8192) v = MPPI_ROLLOUT_LANES16;
-    else if (total <= 32768) v = MPPI_ROLLOUT_LANES8;
+    // Measured on B200 (profiles/exp_lat_r01.txt): one rollout per half-warp wins up to 32768 rollouts (431 us vs
+    // 537 us for the two-rollouts-per-thread kernel), loses at 65536 (838 us vs 630 us).
+    if (total <= 40960) v = MPPI_ROLLOUT_HALF16;
     else v = MPPI_ROLLOUT_THREAD2;
   }
   if (v == MPPI_ROLLOUT_CONST1) v = MPPI_ROLLOUT_THREAD2;  // constant-bank weights measured no faster (profiles/microbench_r01.txt)
@@ -149,6 +149,7 @@ cudaError_t launch_rollout(mppi_ctx *c) {
     case MPPI_ROLLOUT_LANES8: return launch_rollout_nn32_lanes(p, c->stream, 8);
     case MPPI_ROLLOUT_LANES16: return launch_rollout_nn32_lanes(p, c->stream, 16);
     case MPPI_ROLLOUT_LANES32: return launch_rollout_nn32_lanes(p, c->stream, 32);
+    case MPPI_ROLLOUT_HALF16: return launch_rollout_nn32_half(p, c->stream);
     default: return launch_rollout_nn32_r1(p, c->stream, small);
   }
 }
@@ -186,6 +187,7 @@ cudaError_t launch_finalize(mppi_ctx *c, const float *gathered, int G, int last_
   p.gathered = gathered; p.inbox = c->d_inbox; p.outbox = c->d_outbox; p.theta_t = c->d_theta_t;
   p.net_structure = c->d_net_structure;
   p.num_layers = c->cfg.dynamics == MPPI_DYNAMICS_BF ? 0 : (int)c->net_structure.size();
+  p.is_nn32 = (c->cfg.dynamics == MPPI_DYNAMICS_NN && c->net_kind == 32) ? 1 : 0;
   p.G = G; p.B = c->B; p.T = c->T; p.shard_floats = c->shard_floats; p.inbox_stride = c->inbox_stride;
   p.outbox_stride = c->outbox_stride; p.gamma = c->gamma; p.dt = c->dt;
   p.lo0 = c->ranges[0]; p.hi0 = c->ranges[1]; p.lo1 = c->ranges[2]; p.hi1 = c->ranges[3];

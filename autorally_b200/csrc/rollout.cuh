@@ -8,52 +8,75 @@
 
 namespace mppi {
 
-// MPPICosts::computeCost (PI/costs.cu:396-409) with its parts (:307-393).  The track cost runs
-// before the crash cost, so a boundary hit is charged in the same step; `crash` is sticky.
-__device__ __forceinline__ float running_cost_step(const DevCostParams &cp, cudaTextureObject_t tex,
-                                                   const float (&s)[S_DIM], float u0, float u1, float du0,
-                                                   float du1, float nu0, float nu1, int &crash) {
+// The pieces of MPPICosts::computeCost (PI/costs.cu:396-409, parts :307-393) that do not depend on the sticky crash
+// flag.  Two exact shortcuts, both uniform branches on kernel parameters:
+//   * both control-cost coefficients zero (the launch-file default): the term is (+-0)/nu^2 added to +0 = +0;
+//   * an affine costmap transform (r_c1.z = r_c2.z = 0, trs.z = 1, what loadTrackData builds, PI/costs.cu:226-229):
+//     w is exactly 1 and u/w, v/w are u, v, so the four IEEE divisions are skipped.
+struct StepCostParts {
+  float pre;    // control + speed (summed before the crash cost, PI/costs.cu:403)
+  float track;  // track cost
+  float stab;   // stabilizing cost
+  bool boundary;
+};
+
+__device__ __forceinline__ float costmap_lookup(const DevCostParams &cp, cudaTextureObject_t tex, float x, float y) {
+  const float uu = __fadd_rn(fmaf(cp.c1x, x, __fmul_rn(cp.c2x, y)), cp.tx);  // coorTransform, PI/costs.cu:351-357
+  const float vv = __fadd_rn(fmaf(cp.c1y, x, __fmul_rn(cp.c2y, y)), cp.ty);
+  if (cp.affine) return tex2D<float>(tex, uu, vv);
+  const float ww = __fadd_rn(fmaf(cp.c1z, x, __fmul_rn(cp.c2z, y)), cp.tz);
+  return tex2D<float>(tex, __fdiv_rn(uu, ww), __fdiv_rn(vv, ww));
+}
+
+__device__ __forceinline__ StepCostParts step_cost_parts(const DevCostParams &cp, cudaTextureObject_t tex, float x, float y,
+                                                         float yaw, float vx, float vy, float u0, float u1, float du0,
+                                                         float du1, float nu0, float nu1) {
+  StepCostParts r;
   // control cost (:307-313)
   float control = 0.0f;
-  control = __fadd_rn(control, __fdiv_rn(__fmul_rn(__fmul_rn(cp.steering_coeff, du0), __fsub_rn(u0, du0)), __fmul_rn(nu0, nu0)));
-  control = __fadd_rn(control, __fdiv_rn(__fmul_rn(__fmul_rn(cp.throttle_coeff, du1), __fsub_rn(u1, du1)), __fmul_rn(nu1, nu1)));
-  // track cost (:359-393): front/back of the car with the fast intrinsics the reference uses
-  const float cy = __cosf(s[2]), sy = __sinf(s[2]);
-  const float xf = fmaf(0.5f, cy, s[0]), yf = fmaf(0.5f, sy, s[1]);
-  const float xb = fmaf(-0.5f, cy, s[0]), yb = fmaf(-0.5f, sy, s[1]);
-  float uu = __fadd_rn(fmaf(cp.c1x, xf, __fmul_rn(cp.c2x, yf)), cp.tx);
-  float vv = __fadd_rn(fmaf(cp.c1y, xf, __fmul_rn(cp.c2y, yf)), cp.ty);
-  float ww = __fadd_rn(fmaf(cp.c1z, xf, __fmul_rn(cp.c2z, yf)), cp.tz);
-  const float front = tex2D<float>(tex, __fdiv_rn(uu, ww), __fdiv_rn(vv, ww));
-  uu = __fadd_rn(fmaf(cp.c1x, xb, __fmul_rn(cp.c2x, yb)), cp.tx);
-  vv = __fadd_rn(fmaf(cp.c1y, xb, __fmul_rn(cp.c2y, yb)), cp.ty);
-  ww = __fadd_rn(fmaf(cp.c1z, xb, __fmul_rn(cp.c2z, yb)), cp.tz);
-  const float back = tex2D<float>(tex, __fdiv_rn(uu, ww), __fdiv_rn(vv, ww));
-  float track = __fmul_rn(__fadd_rn(fabsf(front), fabsf(back)), 0.5f);  // "/2.0" in double is exact
-  track = (fabsf(track) < cp.track_slop) ? 0.0f : __fmul_rn(cp.track_coeff, track);
-  if (front >= cp.boundary_threshold || back >= cp.boundary_threshold) crash = 1;
+  if (cp.has_control_cost) {
+    control = __fadd_rn(control, __fdiv_rn(__fmul_rn(__fmul_rn(cp.steering_coeff, du0), __fsub_rn(u0, du0)), __fmul_rn(nu0, nu0)));
+    control = __fadd_rn(control, __fdiv_rn(__fmul_rn(__fmul_rn(cp.throttle_coeff, du1), __fsub_rn(u1, du1)), __fmul_rn(nu1, nu1)));
+  }
+  // track cost (:359-393): front / back of the car with the fast intrinsics the reference uses
+  const float cy = __cosf(yaw), sy = __sinf(yaw);
+  const float front = costmap_lookup(cp, tex, fmaf(0.5f, cy, x), fmaf(0.5f, sy, y));
+  const float back = costmap_lookup(cp, tex, fmaf(-0.5f, cy, x), fmaf(-0.5f, sy, y));
+  const float track = __fmul_rn(__fadd_rn(fabsf(front), fabsf(back)), 0.5f);  // "/2.0" in double is exact
+  r.track = (fabsf(track) < cp.track_slop) ? 0.0f : __fmul_rn(cp.track_coeff, track);
+  r.boundary = (front >= cp.boundary_threshold || back >= cp.boundary_threshold);
   // speed cost (:315-326)
-  const float err = __fsub_rn(s[4], cp.desired_speed);
+  const float err = __fsub_rn(vx, cp.desired_speed);
   const float sc = cp.l1_cost ? fabsf(err) : __fmul_rn(err, err);
-  const float speed = __fmul_rn(cp.speed_coeff, sc);
-  // crash cost (:328-335, :402)
-  const float crash_cost = crash > 0 ? cp.crash_cost_on : 0.0f;
+  r.pre = __fadd_rn(control, __fmul_rn(cp.speed_coeff, sc));
   // stabilizing cost (:337-349); the reference compares |u_x| against the double 0.001
   float stab = 0.0f;
-  if (fabsf(s[4]) >= 0.001f) {  // |u_x| > 0.001 (double)  <=>  |u_x| >= 0.001f because 0.001f > 0.001
-    const float slip = -atanf(__fdiv_rn(s[5], fabsf(s[4])));
+  if (fabsf(vx) >= 0.001f) {  // |u_x| > 0.001 (double)  <=>  |u_x| >= 0.001f because 0.001f > 0.001
+    const float slip = -atanf(__fdiv_rn(vy, fabsf(vx)));
     stab = __fmul_rn(cp.slip_penalty, __fmul_rn(slip, slip));
     if (fabsf(slip) > cp.max_slip_ang) stab = __fadd_rn(stab, cp.crash_coeff);
   }
-  float cost = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(control, speed), crash_cost), track), stab);
+  r.stab = stab;
+  return r;
+}
+
+// MPPICosts::computeCost: the track cost runs before the crash cost, so a boundary hit is charged in the same
+// step; `crash` is sticky.
+__device__ __forceinline__ float running_cost_step(const DevCostParams &cp, cudaTextureObject_t tex,
+                                                   const float (&s)[S_DIM], float u0, float u1, float du0,
+                                                   float du1, float nu0, float nu1, int &crash) {
+  const StepCostParts c = step_cost_parts(cp, tex, s[0], s[1], s[2], s[4], s[5], u0, u1, du0, du1, nu0, nu1);
+  if (c.boundary) crash = 1;
+  const float crash_cost = crash > 0 ? cp.crash_cost_on : 0.0f;  // (:328-335, :402)
+  float cost = __fadd_rn(__fadd_rn(__fadd_rn(c.pre, crash_cost), c.track), c.stab);
   if (cost > 1e12f || isnan(cost)) cost = 1e12f;
   return cost;
 }
 
 // One thread owns DYN::R consecutive rollouts.  Grid covers B * n_local rollouts; n_local is a
 // multiple of 64, so a warp never straddles two controllers and is either fully valid or idle.
-template <class DYN, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ RolloutParams p) {
+template <class DYN, int BLOCK, int MINB = 1>
+__global__ void __launch_bounds__(BLOCK, MINB) rollout_kernel(const __grid_constant__ RolloutParams p) {
   constexpr int R = DYN::R;
   extern __shared__ float4 smem4[];
   float *sw = reinterpret_cast<float *>(smem4);

@@ -31,48 +31,6 @@ constexpr int kW1 = 0, kB1 = 192, kW2 = 224, kB2 = 1248, kW3 = 1280, kB3 = 1408;
 constexpr int kBlock = 128;
 constexpr int kMaxT = 512;  // nominal controls / reciprocal table staged in shared memory up to this T
 
-struct StepCostParts {
-  float pre;    // control + speed (summed before the crash cost, PI/costs.cu:403)
-  float track;  // track cost
-  float stab;   // stabilizing cost
-  bool boundary;
-};
-
-// The pieces of MPPICosts::computeCost that do not depend on the sticky crash flag.
-__device__ __forceinline__ StepCostParts step_cost_parts(const DevCostParams &cp, cudaTextureObject_t tex, float x, float y,
-                                                         float yaw, float vx, float vy, float u0, float u1, float du0,
-                                                         float du1, float nu0, float nu1) {
-  StepCostParts r;
-  float control = 0.0f;
-  control = __fadd_rn(control, __fdiv_rn(__fmul_rn(__fmul_rn(cp.steering_coeff, du0), __fsub_rn(u0, du0)), __fmul_rn(nu0, nu0)));
-  control = __fadd_rn(control, __fdiv_rn(__fmul_rn(__fmul_rn(cp.throttle_coeff, du1), __fsub_rn(u1, du1)), __fmul_rn(nu1, nu1)));
-  const float cy = __cosf(yaw), sy = __sinf(yaw);
-  const float xf = fmaf(0.5f, cy, x), yf = fmaf(0.5f, sy, y);
-  const float xb = fmaf(-0.5f, cy, x), yb = fmaf(-0.5f, sy, y);
-  float uu = __fadd_rn(fmaf(cp.c1x, xf, __fmul_rn(cp.c2x, yf)), cp.tx);
-  float vv = __fadd_rn(fmaf(cp.c1y, xf, __fmul_rn(cp.c2y, yf)), cp.ty);
-  float ww = __fadd_rn(fmaf(cp.c1z, xf, __fmul_rn(cp.c2z, yf)), cp.tz);
-  const float front = tex2D<float>(tex, __fdiv_rn(uu, ww), __fdiv_rn(vv, ww));
-  uu = __fadd_rn(fmaf(cp.c1x, xb, __fmul_rn(cp.c2x, yb)), cp.tx);
-  vv = __fadd_rn(fmaf(cp.c1y, xb, __fmul_rn(cp.c2y, yb)), cp.ty);
-  ww = __fadd_rn(fmaf(cp.c1z, xb, __fmul_rn(cp.c2z, yb)), cp.tz);
-  const float back = tex2D<float>(tex, __fdiv_rn(uu, ww), __fdiv_rn(vv, ww));
-  float track = __fmul_rn(__fadd_rn(fabsf(front), fabsf(back)), 0.5f);
-  r.track = (fabsf(track) < cp.track_slop) ? 0.0f : __fmul_rn(cp.track_coeff, track);
-  r.boundary = (front >= cp.boundary_threshold || back >= cp.boundary_threshold);
-  const float err = __fsub_rn(vx, cp.desired_speed);
-  const float sc = cp.l1_cost ? fabsf(err) : __fmul_rn(err, err);
-  r.pre = __fadd_rn(control, __fmul_rn(cp.speed_coeff, sc));
-  float stab = 0.0f;
-  if (fabsf(vx) >= 0.001f) {
-    const float slip = -atanf(__fdiv_rn(vy, fabsf(vx)));
-    stab = __fmul_rn(cp.slip_penalty, __fmul_rn(slip, slip));
-    if (fabsf(slip) > cp.max_slip_ang) stab = __fadd_rn(stab, cp.crash_coeff);
-  }
-  r.stab = stab;
-  return r;
-}
-
 template <int L>
 __global__ void __launch_bounds__(kBlock) rollout_lanes_kernel(const __grid_constant__ RolloutParams p) {
   constexpr int NPL = 32 / L;        // hidden neurons per lane

@@ -7,6 +7,7 @@
 #pragma once
 #include "device_common.cuh"
 #include "dynamics.cuh"
+#include "warp_mlp.cuh"
 
 namespace mppi {
 
@@ -186,6 +187,7 @@ struct FinalizeParams {
   const float *theta_t;   // NN: transposed packed weights; BF: theta 4x25
   const int *net_structure;
   int num_layers;         // NN: entries of net_structure; 0 = basis-function model
+  int is_nn32;            // the 6-32-32-4 network: nominal trajectory on the WarpMlp32 fast path
   int G, B, T, shard_floats, inbox_stride, outbox_stride;
   float gamma, dt, lo0, hi0, lo1, hi1;
   int negate_yaw;
@@ -205,62 +207,34 @@ __device__ __forceinline__ void car_basis_host_twin(const float *theta, const fl
   for (int j = 0; j < 4; j++) out4[j] = o[j][0];
 }
 
-// Nominal trajectory for the 6-32-32-4 network on ONE warp (computeNominalTraj, PI/mppi_controller.cu:501-519).
-// Lane j owns hidden neuron j of both hidden layers with its weights in registers; activations cross
-// lanes through shared memory; layer 2 uses 4 interleaved partial sums (8 FMAs deep instead of 32) and
-// layer 3 is (4 outputs) x (8 chunks) with a xor tree, so one step is a ~300-cycle dependent chain.
-// x / y need sincosf(yaw) only for the OUTPUT, so they are filled in 32 steps at a time by all lanes in
-// parallel (sequential FMA prefix, the reference's Euler order).  Within the 1e-4 parity tolerance of
-// the host twin (FMA contraction and tanh_fast differ from Eigen/libm in the last bits).
-__device__ __forceinline__ void nominal_traj_nn32(const float *__restrict__ sw, const float *__restrict__ inbox,
+// Nominal trajectory for the 6-32-32-4 network on ONE warp (computeNominalTraj, PI/mppi_controller.cu:501-519):
+// WarpMlp32 (warp_mlp.cuh) advances the recursive state; x / y need sincosf(yaw) only for the OUTPUT, so they are
+// filled in 32 steps at a time by all lanes in parallel (sequential FMA prefix, the reference's Euler order).
+// Within the 1e-4 parity tolerance of the host twin (FMA contraction, partial sums and tanh_fast differ from
+// Eigen/libm in the last bits).
+__device__ __forceinline__ void nominal_traj_nn32(const WarpMlp32 &net, const float *__restrict__ inbox,
                                                   const float *__restrict__ Usm, int T, float dt, int negate_yaw, float lo0,
                                                   float hi0, float lo1, float hi1, float *__restrict__ ssol,
                                                   float *__restrict__ csol, float *__restrict__ act, int lane) {
-  constexpr int kW1 = 0, kB1 = 192, kW2 = 224, kB2 = 1248, kW3 = 1280, kB3 = 1408;
   const unsigned full = 0xffffffffu;
-  float w1[6], w2[32], w3[4];
-#pragma unroll
-  for (int k = 0; k < 6; k++) w1[k] = sw[kW1 + k * 32 + lane];
-#pragma unroll
-  for (int k = 0; k < 32; k++) w2[k] = sw[kW2 + k * 32 + lane];
-  const int jo = lane & 3, chunk = lane >> 2;
-#pragma unroll
-  for (int kk = 0; kk < 4; kk++) w3[kk] = sw[kW3 + (chunk * 4 + kk) * 4 + jo];
-  const float b1 = sw[kB1 + lane], b2 = sw[kB2 + lane], b3 = sw[kB3 + jo];
   float x = inbox[INBOX_STATE + 0], y = inbox[INBOX_STATE + 1], yaw = inbox[INBOX_STATE + 2];
   float roll = inbox[INBOX_STATE + 3], vx = inbox[INBOX_STATE + 4], vy = inbox[INBOX_STATE + 5], wz = inbox[INBOX_STATE + 6];
-  float *h1 = act, *h2 = act + 64;
   for (int i0 = 0; i0 < T; i0 += 32) {
     const int nb = min(32, T - i0);
+    // this lane's timestep: clamp the control (enforceConstraints) and publish it
+    float u0m = 0.0f, u1m = 0.0f;
+    if (lane < nb) {
+      u0m = Usm[2 * (i0 + lane)]; u1m = Usm[2 * (i0 + lane) + 1];
+      u0m = u0m < lo0 ? lo0 : (u0m > hi0 ? hi0 : u0m);
+      u1m = u1m < lo1 ? lo1 : (u1m > hi1 ? hi1 : u1m);
+      csol[2 * (i0 + lane)] = u0m; csol[2 * (i0 + lane) + 1] = u1m;
+    }
     float r_yaw = 0.0f, r_roll = 0.0f, r_vx = 0.0f, r_vy = 0.0f, r_wz = 0.0f;
     for (int ii = 0; ii < nb; ii++) {
-      const int i = i0 + ii;
-      float u0 = Usm[2 * i], u1 = Usm[2 * i + 1];
-      u0 = u0 < lo0 ? lo0 : (u0 > hi0 ? hi0 : u0);
-      u1 = u1 < lo1 ? lo1 : (u1 > hi1 ? hi1 : u1);
-      if (lane == ii) { r_yaw = yaw; r_roll = roll; r_vx = vx; r_vy = vy; r_wz = wz; csol[2 * i] = u0; csol[2 * i + 1] = u1; }
-      float t = w1[0] * roll;
-      t = fmaf(w1[1], vx, t); t = fmaf(w1[2], vy, t); t = fmaf(w1[3], wz, t); t = fmaf(w1[4], u0, t); t = fmaf(w1[5], u1, t);
-      float *hb = h1 + (i & 1) * 32;
-      hb[lane] = tanh_fast(t + b1);
-      __syncwarp();
-      float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-#pragma unroll
-      for (int k4 = 0; k4 < 8; k4++) {
-        const float4 hv = reinterpret_cast<const float4 *>(hb)[k4];
-        a0 = fmaf(w2[4 * k4 + 0], hv.x, a0); a1 = fmaf(w2[4 * k4 + 1], hv.y, a1);
-        a2 = fmaf(w2[4 * k4 + 2], hv.z, a2); a3 = fmaf(w2[4 * k4 + 3], hv.w, a3);
-      }
-      float *gb = h2 + (i & 1) * 32;
-      gb[lane] = tanh_fast(((a0 + a1) + (a2 + a3)) + b2);
-      __syncwarp();
-      const float4 gv = reinterpret_cast<const float4 *>(gb)[chunk];
-      float part = w3[0] * gv.x;
-      part = fmaf(w3[1], gv.y, part); part = fmaf(w3[2], gv.z, part); part = fmaf(w3[3], gv.w, part);
-      part += __shfl_xor_sync(full, part, 4); part += __shfl_xor_sync(full, part, 8); part += __shfl_xor_sync(full, part, 16);
-      part += b3;
-      const float o0 = __shfl_sync(full, part, 0), o1 = __shfl_sync(full, part, 1);
-      const float o2 = __shfl_sync(full, part, 2), o3 = __shfl_sync(full, part, 3);
+      const float u0 = __shfl_sync(full, u0m, ii), u1 = __shfl_sync(full, u1m, ii);
+      if (lane == ii) { r_yaw = yaw; r_roll = roll; r_vx = vx; r_vy = vy; r_wz = wz; }
+      float o0, o1, o2, o3;
+      net.forward(roll, vx, vy, wz, u0, u1, act, ii & 1, lane, o0, o1, o2, o3);
       yaw = fmaf(negate_yaw ? -wz : wz, dt, yaw);
       roll = fmaf(o0, dt, roll); vx = fmaf(o1, dt, vx); vy = fmaf(o2, dt, vy); wz = fmaf(o3, dt, wz);
     }
@@ -296,6 +270,9 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ F
   __shared__ float hdr[4];
   float *inbox = p.inbox + (size_t)b * p.inbox_stride;
   float *outbox = p.outbox + (size_t)b * p.outbox_stride;
+  // warp 0 fetches its slices of the network while the other warps combine the shard records
+  WarpMlp32 net;
+  if (p.is_nn32 && p.last_iter && tid < 32) net.load(p.theta_t, tid);
 
   if (tid == 0) {
     float base = p.gathered[((size_t)0 * p.B + b) * p.shard_floats];
@@ -346,13 +323,15 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ F
     Usm[k] = acc;
     outbox[4 + k] = acc;
   }
-  // stage the model parameters for the nominal trajectory
-  int nparams = 100;
-  if (p.num_layers > 0) {
-    nparams = 0;
-    for (int l = 0; l + 1 < p.num_layers; l++) nparams += (p.net_structure[l] + 1) * p.net_structure[l + 1];
+  // stage the model parameters for the generic nominal trajectory (the 6-32-32-4 path holds them in registers)
+  if (!p.is_nn32) {
+    int nparams = 100;
+    if (p.num_layers > 0) {
+      nparams = 0;
+      for (int l = 0; l + 1 < p.num_layers; l++) nparams += (p.net_structure[l] + 1) * p.net_structure[l + 1];
+    }
+    for (int k = tid; k < nparams; k += 256) sw[k] = p.theta_t[k];
   }
-  for (int k = tid; k < nparams; k += 256) sw[k] = p.theta_t[k];
   __syncthreads();
   if (p.feed_back)
     for (int k = tid; k < 2 * T; k += 256) inbox[INBOX_U + k] = Usm[k];
@@ -361,8 +340,8 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ F
   const int lane = tid;
   float *ssol = outbox + 4 + 4 * T;
   float *csol = ssol + S_DIM * T;
-  if (p.num_layers == 4 && p.net_structure[0] == 6 && p.net_structure[1] == 32 && p.net_structure[2] == 32 && p.net_structure[3] == 4) {
-    nominal_traj_nn32(sw, inbox, Usm, T, p.dt, p.negate_yaw, p.lo0, p.hi0, p.lo1, p.hi1, ssol, csol, act, lane);
+  if (p.is_nn32) {
+    nominal_traj_nn32(net, inbox, Usm, T, p.dt, p.negate_yaw, p.lo0, p.hi0, p.lo1, p.hi1, ssol, csol, act, lane);
     return;
   }
   float s[S_DIM];

@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--dynamics", default="nn")
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--controllers", type=int, default=1)
+    ap.add_argument("--timesteps", type=int, default=100)
     a = ap.parse_args()
     from autorally_b200.params import ellipse_states, make_ellipse_costmap
     from tests.common import cost_params_for, default_state, make_context, warm_controls
@@ -27,8 +28,9 @@ def main():
     cp = cost_params_for(costmap)
     B = a.controllers
     state = default_state(5.0) if B == 1 else ellipse_states(B)
-    U = warm_controls(100) if B == 1 else np.broadcast_to(warm_controls(100), (B, 100, 2)).copy()
-    with make_context(a.dynamics, models, costmap, cp, a.rollouts, variant=a.variant, num_controllers=B) as ctx:
+    T = a.timesteps
+    U = warm_controls(T) if B == 1 else np.broadcast_to(warm_controls(T), (B, T, 2)).copy()
+    with make_context(a.dynamics, models, costmap, cp, a.rollouts, variant=a.variant, num_controllers=B, num_timesteps=T) as ctx:
         out = ctx.compute_control(state, U)
         ms, rk = ctx.run_resident(a.steps, time_rollout=True)
         print("variant", ctx.resolved_variant(), "ms/step", ms / a.steps, "rollout kernel ms", rk / a.steps)
