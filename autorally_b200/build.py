@@ -62,11 +62,16 @@ def build_library(force=False, verbose=False):
 
 
 def build_host_tests(force=False):
-    """Compiles the C++ host-layer test driver (include/autorally_control/path_integral/*) if present."""
-    src = os.path.join(ROOT, "tests", "cpp", "host_api_driver.cu")
+    """Compiles the C++ host-layer test drivers (include/autorally_control/path_integral/*)."""
+    outs = [_build_driver(name, force) for name in ("host_api_driver", "control_loop_driver")]
+    return outs[0]
+
+
+def _build_driver(name, force=False):
+    src = os.path.join(ROOT, "tests", "cpp", name + ".cu")
     if not os.path.exists(src):
         return None
-    out = os.path.join(LIB_DIR, "host_api_driver")
+    out = os.path.join(LIB_DIR, name)
     deps = [src, LIB]
     inc = os.path.join(ROOT, "include")
     for d, _, fs in os.walk(inc):

@@ -1,0 +1,67 @@
+// sim_plant.h -- SimPlant: an in-process stand-in for AutorallyPlant (PI/autorally_plant.h:165-256) with the methods
+// runControlLoop calls.  The reference's plant is the ROS I/O node (pose / servo subscribers, chassisCommand
+// publisher); here the "robot" is whatever the loop itself integrates in debug mode
+// (PI/run_control_loop.cuh:296-302: the host dynamics model is the plant), and SimPlant only keeps the bookkeeping:
+// the last solution handed over, the executed state / control log, timing averages, pending parameter updates.
+#ifndef MPPI_SIM_PLANT_H_
+#define MPPI_SIM_PLANT_H_
+#include <vector>
+
+#include "costs.cuh"
+
+namespace autorally_control {
+
+enum class ControllerType { NONE, ACTUAL_STATE, PREDICTED_STATE };
+
+class SimPlant {
+ public:
+  struct FullState {
+    float x_pos = 0, y_pos = 0, z_pos = 0, roll = 0, pitch = 0, yaw = 0, q0 = 1, q1 = 0, q2 = 0, q3 = 0;
+    float x_vel = 0, y_vel = 0, z_vel = 0, u_x = 0, u_y = 0, yaw_mder = 0, steering = 0, throttle = 0;
+  };
+
+  SimPlant(float x, float y, float yaw) { full_state_.x_pos = x; full_state_.y_pos = y; full_state_.yaw = yaw; }
+
+  // ---- what runControlLoop uses ----
+  double getLastPoseTime() const { return last_pose_time_; }
+  FullState getState() const { return full_state_; }
+  void setTimingInfo(double avg_loop, double avg_tick, double avg_sleep) { avg_loop_ = avg_loop; avg_tick_ = avg_tick; avg_sleep_ = avg_sleep; }
+  bool hasNewDynRcfg() const { return has_dcfg_; }
+  PathIntegralParamsConfig getDynRcfgParams() { has_dcfg_ = false; return dcfg_; }
+  bool hasNewObstacles() const { return false; }
+  void getObstacles(std::vector<int> &, std::vector<float> &) {}
+  bool hasNewCostmap() const { return false; }
+  void getCostmap(std::vector<int> &, std::vector<float> &) {}
+  bool hasNewModel() const { return has_model_; }
+  void getModel(std::vector<int> &description, std::vector<float> &data) { description = model_description_; data = model_data_; has_model_ = false; }
+  template <class GAINS>
+  void setSolution(const std::vector<float> &state_seq, const std::vector<float> &control_seq, const GAINS &, double ts,
+                   double loop_speed, ControllerType used) {
+    state_seq_ = state_seq; control_seq_ = control_seq; solution_ts_ = ts; (void)loop_speed;
+    executed_states_.insert(executed_states_.end(), state_seq.begin(), state_seq.begin() + 7);
+    executed_controls_.insert(executed_controls_.end(), control_seq.begin(), control_seq.begin() + 2);
+    controller_used_.push_back(used == ControllerType::ACTUAL_STATE ? 0 : 1);
+  }
+  /// 1 = "no pose updates: integrate the model" -- the reference's status for debug mode (PI/run_control_loop.cuh:296)
+  int checkStatus() const { return 1; }
+  template <class IMG> void setDebugImage(const IMG &) {}
+
+  // ---- test / driver side ----
+  void pushDynRcfg(const PathIntegralParamsConfig &c) { dcfg_ = c; has_dcfg_ = true; }
+  void pushModel(const std::vector<int> &description, const std::vector<float> &data) { model_description_ = description; model_data_ = data; has_model_ = true; }
+  const std::vector<float> &executedStates() const { return executed_states_; }      // [iterations][7]
+  const std::vector<float> &executedControls() const { return executed_controls_; }  // [iterations][2]
+  const std::vector<int> &controllerUsed() const { return controller_used_; }
+  double avgTickMs() const { return avg_tick_; }
+
+ private:
+  FullState full_state_;
+  double last_pose_time_ = 0.0, solution_ts_ = 0.0, avg_loop_ = 0, avg_tick_ = 0, avg_sleep_ = 0;
+  bool has_dcfg_ = false, has_model_ = false;
+  PathIntegralParamsConfig dcfg_;
+  std::vector<int> model_description_, controller_used_;
+  std::vector<float> model_data_, state_seq_, control_seq_, executed_states_, executed_controls_;
+};
+
+}  // namespace autorally_control
+#endif
