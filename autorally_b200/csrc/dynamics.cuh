@@ -154,13 +154,72 @@ struct NeuralNetDynP2 {
   static constexpr int WSRC = WSRC_;
   static constexpr int SMEM_FLOATS = WSRC_ == 0 ? NetShape<W...>::NPARAMS : 0;
   static constexpr int NPARAMS = NetShape<W...>::NPARAMS;
-  __device__ __forceinline__ static void deriv(const float *__restrict__ sw, const float (&in)[6][2], float (&out)[4][2]) {
+  static constexpr int THREAD_SMEM_FLOATS = 0;
+  __device__ __forceinline__ static void deriv(const float *__restrict__ sw, float *, const float (&in)[6][2], float (&out)[4][2]) {
     float2 a[6], o[4];
 #pragma unroll
     for (int k = 0; k < 6; k++) a[k] = make_float2(in[k][0], in[k][1]);
     NetChainP2<WSRC_, W...>::forward(sw, 0, a, o);
 #pragma unroll
     for (int k = 0; k < 4; k++) { out[k][0] = o[k].x; out[k][1] = o[k].y; }
+  }
+};
+
+// ---- compact variant of the packed pair: layer 2 as a ROLLED loop over chunks of 8 outputs -----------------------
+// ncu on the fully unrolled pair kernel (profiles/ncu_1m_r01b.txt) shows the instruction fetch as its first stall
+// reason ("no_instruction", 21% of the warp cycles): one timestep is ~2900 straight-line instructions = 46 KB, far
+// beyond the instruction caches, and 168 live registers allow only 3 warps per scheduler to hide it.  Here the 32 x 32
+// layer runs as 4 iterations of one 8-output body (64 LDS.128 + 256 FFMA2 + 8 bias / tanh): its outputs go to a
+// per-thread shared-memory column (dynamic index, which registers cannot do) from which layer 3 reads them back.
+// k still ascends from 0 with FMA and the bias is added last, so results are bit-identical to NetChainP2.
+// Cost: 32 STS.64 + 32 LDS.64 per timestep; gain: ~1000 fewer instructions of code and 48 fewer live registers.
+template <int BLOCK>
+struct NeuralNetDynP2Compact {
+  static constexpr int R = 2;
+  static constexpr int SMEM_FLOATS = NetShape<6, 32, 32, 4>::NPARAMS;
+  static constexpr int THREAD_SMEM_FLOATS = 64;  // h2[32] as float2, laid out [j][thread]
+  static constexpr int kW2 = 224, kB2 = 1248, kW3 = 1280, kB3 = 1408;
+  __device__ __forceinline__ static void deriv(const float *__restrict__ sw, float *__restrict__ tsm, const float (&in)[6][2],
+                                               float (&out)[4][2]) {
+    float2 a[6], h1[32];
+#pragma unroll
+    for (int k = 0; k < 6; k++) a[k] = make_float2(in[k][0], in[k][1]);
+    dense_layer_p2<6, 32, true, 0>(sw, 0, a, h1);
+    float2 *h2 = reinterpret_cast<float2 *>(tsm);
+#pragma unroll 1
+    for (int c = 0; c < 4; c++) {
+      const float4 *W = reinterpret_cast<const float4 *>(sw + kW2 + 8 * c);
+      float2 o[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) o[j] = make_float2(0.0f, 0.0f);
+#pragma unroll
+      for (int k = 0; k < 32; k++) {
+        const float4 wa = W[k * 8], wb = W[k * 8 + 1];
+        o[0] = __ffma2_rn(make_float2(wa.x, wa.x), h1[k], o[0]); o[1] = __ffma2_rn(make_float2(wa.y, wa.y), h1[k], o[1]);
+        o[2] = __ffma2_rn(make_float2(wa.z, wa.z), h1[k], o[2]); o[3] = __ffma2_rn(make_float2(wa.w, wa.w), h1[k], o[3]);
+        o[4] = __ffma2_rn(make_float2(wb.x, wb.x), h1[k], o[4]); o[5] = __ffma2_rn(make_float2(wb.y, wb.y), h1[k], o[5]);
+        o[6] = __ffma2_rn(make_float2(wb.z, wb.z), h1[k], o[6]); o[7] = __ffma2_rn(make_float2(wb.w, wb.w), h1[k], o[7]);
+      }
+      const float4 ba = *reinterpret_cast<const float4 *>(sw + kB2 + 8 * c), bb = *reinterpret_cast<const float4 *>(sw + kB2 + 8 * c + 4);
+      const float bj[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+      for (int j = 0; j < 8; j++) h2[(8 * c + j) * BLOCK] = tanh_fast2(__fadd2_rn(o[j], make_float2(bj[j], bj[j])));
+    }
+    float2 y[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) y[j] = make_float2(0.0f, 0.0f);
+#pragma unroll
+    for (int k = 0; k < 32; k++) {
+      const float2 g = h2[k * BLOCK];
+      const float4 w = reinterpret_cast<const float4 *>(sw + kW3)[k];
+      y[0] = __ffma2_rn(make_float2(w.x, w.x), g, y[0]); y[1] = __ffma2_rn(make_float2(w.y, w.y), g, y[1]);
+      y[2] = __ffma2_rn(make_float2(w.z, w.z), g, y[2]); y[3] = __ffma2_rn(make_float2(w.w, w.w), g, y[3]);
+    }
+    const float4 b3 = *reinterpret_cast<const float4 *>(sw + kB3);
+    y[0] = __fadd2_rn(y[0], make_float2(b3.x, b3.x)); y[1] = __fadd2_rn(y[1], make_float2(b3.y, b3.y));
+    y[2] = __fadd2_rn(y[2], make_float2(b3.z, b3.z)); y[3] = __fadd2_rn(y[3], make_float2(b3.w, b3.w));
+#pragma unroll
+    for (int k = 0; k < 4; k++) { out[k][0] = y[k].x; out[k][1] = y[k].y; }
   }
 };
 
@@ -171,8 +230,9 @@ struct NeuralNetDyn {
   static constexpr int R = R_;
   static constexpr int SMEM_FLOATS = NetShape<W...>::NPARAMS;
   using Chain = NetChain<R_, W...>;
+  static constexpr int THREAD_SMEM_FLOATS = 0;
   static_assert(NetShape<W...>::FIRST == 6 && NetShape<W...>::LAST == 4, "6 inputs, 4 outputs");
-  __device__ __forceinline__ static void deriv(const float *__restrict__ sw, const float (&in)[6][R_], float (&out)[4][R_]) {
+  __device__ __forceinline__ static void deriv(const float *__restrict__ sw, float *, const float (&in)[6][R_], float (&out)[4][R_]) {
     Chain::forward(sw, in, out);
   }
 };
@@ -180,7 +240,8 @@ struct NeuralNetDyn {
 struct CarBasisDyn {
   static constexpr int R = 1;
   static constexpr int SMEM_FLOATS = 100;  // theta 4 x 25 row-major
-  __device__ __forceinline__ static void deriv(const float *__restrict__ sw, const float (&in)[6][1], float (&out)[4][1]) {
+  static constexpr int THREAD_SMEM_FLOATS = 0;
+  __device__ __forceinline__ static void deriv(const float *__restrict__ sw, float *, const float (&in)[6][1], float (&out)[4][1]) {
     const float roll = in[0][0], vx = in[1][0], vy = in[2][0], wz = in[3][0], steer = in[4][0], thr = in[5][0];
     const bool moving = vx >= 0.1f;  // (double)vx > .1  <=>  vx >= 0.1f because 0.1f > 0.1
     const float ratio_y = __fdiv_rn(vy, vx);

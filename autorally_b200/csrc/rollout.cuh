@@ -82,6 +82,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) rollout_kernel(const __grid_const
   float *sw = reinterpret_cast<float *>(smem4);
   for (int i = threadIdx.x; i < DYN::SMEM_FLOATS / 4; i += BLOCK) smem4[i] = reinterpret_cast<const float4 *>(p.theta_t)[i];
   __syncthreads();
+  // per-thread staging column (policies that need dynamically indexed storage), [slot][thread] after the weights
+  float *tsm = sw + ((DYN::SMEM_FLOATS + 3) & ~3) + (DYN::THREAD_SMEM_FLOATS ? 2 * threadIdx.x : 0);
 
   const long long total = (long long)p.B * p.n_local;
   const long long g0 = ((long long)blockIdx.x * BLOCK + threadIdx.x) * R;
@@ -141,7 +143,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) rollout_kernel(const __grid_const
         in[4][r] = u[r][0]; in[5][r] = u[r][1];
       }
       float dyn_out[4][R];
-      DYN::deriv(sw, in, dyn_out);
+      DYN::deriv(sw, tsm, in, dyn_out);
 #pragma unroll
       for (int r = 0; r < R; r++) {
         // kinematics, PI/neural_net_model.cu:346-355 (precise sinf/cosf)

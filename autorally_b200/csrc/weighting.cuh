@@ -203,7 +203,7 @@ constexpr int FIN_MAX_WIDTH = 128;
 __device__ __forceinline__ void car_basis_host_twin(const float *theta, const float *s, float u0, float u1, float *out4) {
   float in[6][1] = {{s[3]}, {s[4]}, {s[5]}, {s[6]}, {u0}, {u1}};
   float o[4][1];
-  CarBasisDyn::deriv(theta, in, o);
+  CarBasisDyn::deriv(theta, nullptr, in, o);
   for (int j = 0; j < 4; j++) out4[j] = o[j][0];
 }
 

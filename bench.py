@@ -54,7 +54,7 @@ def load_setup():
 class ClockSampler:
     """Samples SM clock and throttle reasons through NVML while the timed region runs."""
 
-    def __init__(self, index=0, period=0.05):
+    def __init__(self, index=0, period=0.002):
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
         self._thread = None
@@ -240,6 +240,38 @@ def measure_large(models, costmap, cp, state, U, n_rollouts, r_begin=0, r_count=
     return out
 
 
+def measure_other_configs(models, costmap, cp, world, rank, local_rank, barrier, max_over_ranks):
+    """BASELINE configs[2] (path_integral_bf, 2560 x 100) and configs[4] (batched MPC: 4096 independent controllers x
+    256 rollouts x 100, controllers sharded over the ranks with no communication), device-resident, CUDA events."""
+    from autorally_b200.params import ellipse_states
+    from autorally_b200.sharding import controller_shard
+    from tests.common import cost_params_for, make_context, straight_controls, top_state
+    out = {}
+    cp_bf = cost_params_for(costmap, desired_speed=6.0)
+    with make_context("bf", models, costmap, cp_bf, 2560, device=local_rank) as ctx:
+        ctx.compute_control(top_state(4.0), straight_controls(T_STEPS))
+        ctx.run_resident(3)
+        ms, rk = ctx.run_resident(20, time_rollout=True)
+        out["bf_2560x100"] = {"ms_per_step": ms / 20, "rollout_kernel_ms": rk / 20, "value": 2560 * T_STEPS * 20 / (ms * 1e-3),
+                              "unit": "rollout-steps/s", "note": "per GPU, one controller"}
+    B_total, n = 4096, 256
+    b0, B = controller_shard(rank, world, B_total)
+    states = ellipse_states(B_total)[b0:b0 + B]
+    Ub = np.broadcast_to(straight_controls(T_STEPS), (B, T_STEPS, 2)).copy()
+    with make_context("nn", models, costmap, cp, n, num_controllers=B, device=local_rank) as ctx:
+        ctx.compute_control(states, Ub)
+        ctx.run_resident(1)
+        barrier()
+        ms, rk = ctx.run_resident(3, time_rollout=True)
+        barrier()
+        ms = max_over_ranks(ms)
+        out["batched_4096x256x100"] = {"controllers_per_gpu": B, "ms_per_step": ms / 3, "rollout_kernel_ms": rk / 3,
+                                       "value": B_total * n * T_STEPS * 3 / (ms * 1e-3), "unit": "rollout-steps/s",
+                                       "controllers_per_s": B_total * 3 / (ms * 1e-3),
+                                       "scaling": "strong (4096 controllers split over the ranks, no communication)"}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -346,6 +378,8 @@ def main():
             line["large"] = measure_large(models, costmap, cp, state, U, LARGE_ROLLOUTS, fp32_peak=fp32_peak)
         else:
             line["sharded_large"] = run_sharded_large(models, costmap, cp, state, U, world, rank, local_rank, barrier, max_over_ranks)
+    if not args.no_large:
+        line["other_configs"] = measure_other_configs(models, costmap, cp, world, rank, local_rank, barrier, max_over_ranks)
     if rank == 0 and world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(models, costmap, cp, state, U)
     if rank == 0:
