@@ -36,7 +36,7 @@ EXPORTED_SYMBOLS = [
     "mppi_last_launch_count", "mppi_resolved_variant", "mppi_measure_fp32_peak", "mppi_measure_copy_bandwidth",
     "mppi_shard_begin_async", "mppi_shard_finish_async", "mppi_shard_result", "mppi_set_stream",
     "mppi_comm_unique_id", "mppi_comm_init", "mppi_comm_destroy", "mppi_compute_control_sharded",
-    "mppi_run_resident_sharded",
+    "mppi_run_resident_sharded", "mppi_compute_control_async", "mppi_compute_control_wait",
 ]
 
 
@@ -199,6 +199,19 @@ class MppiContext:
         if B == 1:
             out = {k: v[0] for k, v in out.items()}
         return out
+
+    def compute_control_async(self, state, U, hist=None):
+        B, T = self.B, self.T
+        state, U = _f32(state).reshape(B, 7), _f32(U).reshape(B, T, 2)
+        hist = _f32(hist if hist is not None else np.zeros((B, 4))).reshape(B, 4)
+        self._ck(self.lib.mppi_compute_control_async(self._ctx, _fp(state), _fp(U), _fp(hist)), "mppi_compute_control_async")
+
+    def compute_control_wait(self):
+        B, T = self.B, self.T
+        U, ss, cs = np.zeros((B, T, 2), np.float32), np.zeros((B, T, 7), np.float32), np.zeros((B, T, 2), np.float32)
+        res = (MppiResult * B)()
+        self._ck(self.lib.mppi_compute_control_wait(self._ctx, _fp(U), _fp(ss), _fp(cs), res), "mppi_compute_control_wait")
+        return self._result(U, ss, cs, res)
 
     def rollout_costs(self):
         c = np.zeros((self.B, self.n_local), np.float32)

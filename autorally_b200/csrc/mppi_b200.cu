@@ -537,7 +537,7 @@ static int enqueue_compute(mppi_ctx *c) {
   return MPPI_OK;
 }
 
-int mppi_compute_control(mppi_ctx *c, const float *state, float *U, const float *hist, float *ss, float *cs, mppi_result *res) {
+int mppi_compute_control_async(mppi_ctx *c, const float *state, const float *U, const float *hist) {
   int rc = check_ready(c);
   if (rc) return rc;
   if (!state || !U) return MPPI_ERR_INVALID_ARG;
@@ -569,9 +569,21 @@ int mppi_compute_control(mppi_ctx *c, const float *state, float *U, const float 
     c->launches = c->graph_launches;
     CK(cudaGraphLaunch(c->graph_exec, c->stream));
   }
+  return MPPI_OK;
+}
+
+int mppi_compute_control_wait(mppi_ctx *c, float *U, float *ss, float *cs, mppi_result *res) {
+  if (!c) return MPPI_ERR_INVALID_ARG;
+  CK(cudaSetDevice(c->device));
   CK(cudaStreamSynchronize(c->stream));
   unpack_outbox(c, U, ss, cs, res);
   return MPPI_OK;
+}
+
+int mppi_compute_control(mppi_ctx *c, const float *state, float *U, const float *hist, float *ss, float *cs, mppi_result *res) {
+  int rc = mppi_compute_control_async(c, state, U, hist);
+  if (rc) return rc;
+  return mppi_compute_control_wait(c, U, ss, cs, res);
 }
 
 int mppi_get_rollout_costs(mppi_ctx *c, float *costs) {

@@ -120,13 +120,12 @@ __global__ void __launch_bounds__(256) weight_reduce_kernel(const __grid_constan
     float2 acc = make_float2(0.0f, 0.0f);
     if (rl < nrl && c < T) {
       int i = rl;
-      for (; i + 3 * nrl < nrows; i += 4 * nrl) {
-        const float2 v0 = V[(size_t)i * T + c], v1 = V[(size_t)(i + nrl) * T + c];
-        const float2 v2 = V[(size_t)(i + 2 * nrl) * T + c], v3 = V[(size_t)(i + 3 * nrl) * T + c];
-        acc.x = fmaf(w[i], v0.x, acc.x); acc.y = fmaf(w[i], v0.y, acc.y);
-        acc.x = fmaf(w[i + nrl], v1.x, acc.x); acc.y = fmaf(w[i + nrl], v1.y, acc.y);
-        acc.x = fmaf(w[i + 2 * nrl], v2.x, acc.x); acc.y = fmaf(w[i + 2 * nrl], v2.y, acc.y);
-        acc.x = fmaf(w[i + 3 * nrl], v3.x, acc.x); acc.y = fmaf(w[i + 3 * nrl], v3.y, acc.y);
+      for (; i + 7 * nrl < nrows; i += 8 * nrl) {  // 8 independent row loads in flight, accumulated in row order
+        float2 v[8];
+#pragma unroll
+        for (int m = 0; m < 8; m++) v[m] = V[(size_t)(i + m * nrl) * T + c];
+#pragma unroll
+        for (int m = 0; m < 8; m++) { acc.x = fmaf(w[i + m * nrl], v[m].x, acc.x); acc.y = fmaf(w[i + m * nrl], v[m].y, acc.y); }
       }
       for (; i < nrows; i += nrl) {
         const float2 v = V[(size_t)i * T + c];
@@ -166,8 +165,17 @@ __global__ void __launch_bounds__(256) weight_reduce_kernel(const __grid_constan
   for (int k = tid; k < p.shard_floats; k += 256) {
     if (k == 0) { shard[0] = base; continue; }
     if (k == 3 || k >= SHARD_HDR + 2 * T) { shard[k] = 0.0f; continue; }
+    // 16 independent L2 loads in flight per thread (the partials were just written by other SMs); the summation
+    // order is fixed, so the result is bitwise reproducible run to run
     float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
     int j = 0;
+    for (; j + 15 < p.nblk; j += 16) {
+      float v[16];
+#pragma unroll
+      for (int m = 0; m < 16; m++) v[m] = __ldcg(parts + (size_t)(j + m) * p.shard_floats + k);
+#pragma unroll
+      for (int m = 0; m < 16; m += 4) { a0 += v[m]; a1 += v[m + 1]; a2 += v[m + 2]; a3 += v[m + 3]; }
+    }
     for (; j + 3 < p.nblk; j += 4) {
       a0 += __ldcg(parts + (size_t)j * p.shard_floats + k);
       a1 += __ldcg(parts + (size_t)(j + 1) * p.shard_floats + k);

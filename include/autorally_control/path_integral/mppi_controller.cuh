@@ -192,6 +192,30 @@ class MPPIController {
     }
   }
 
+  /// Extension: the two halves of computeControl(state).  computeControlAsync enqueues the whole hot path on this
+  /// controller's stream and returns; waitControl blocks and stores the results.  Two controllers started back to back
+  /// run concurrently on the GPU (run_control_loop.cuh uses this for the actual- / predicted-state pair).
+  void computeControlAsync(Eigen::Matrix<float, DYNAMICS_T::STATE_DIM, 1> state) {
+    if (!ctx_) return;
+    syncParams();
+    float st[DYNAMICS_T::STATE_DIM];
+    for (int i = 0; i < STATE_DIM; i++) st[i] = state(i);
+    pending_rc_ = mppi_compute_control_async(ctx_, st, U_.data(), control_hist_.data());
+    HANDLE_ERROR(pending_rc_);
+  }
+  void computeControlAsync() {
+    Eigen::Matrix<float, DYNAMICS_T::STATE_DIM, 1> expected;
+    for (int i = 0; i < STATE_DIM; i++) expected(i) = state_solution_[i];
+    computeControlAsync(expected);
+  }
+  void waitControl() {
+    if (!ctx_ || pending_rc_ != 0) return;
+    mppi_result res;
+    const int rc = mppi_compute_control_wait(ctx_, U_.data(), state_solution_.data(), control_solution_.data(), &res);
+    HANDLE_ERROR(rc);
+    if (rc == 0) { normalizer_ = res.normalizer; trajectory_cost_ = res.trajectory_cost; baseline_ = res.baseline; }
+  }
+
   std::vector<float> getControlSeq() { return control_solution_; }
   std::vector<float> getStateSeq() { return state_solution_; }
   float getComputedTrajectoryCost() { return trajectory_cost_; }
@@ -259,6 +283,7 @@ class MPPIController {
   int num_iters_;
   float gamma_;
   float normalizer_ = 0, trajectory_cost_ = 0, baseline_ = 0;
+  int pending_rc_ = 0;
   std::vector<float> traj_costs_, state_solution_, control_solution_, control_hist_, U_, du_, nu_, init_u_;
   mppi_ctx *ctx_ = nullptr;
   unsigned long model_version_ = ~0ul, costs_version_ = ~0ul, map_version_ = ~0ul;

@@ -105,9 +105,12 @@ void runControlLoop(CONTROLLER_T *predicted_state_controller, CONTROLLER_T *actu
       actual_state_controller->slideControlAndStateSeq(stride);
       predicted_state_controller->slideControlAndStateSeq(stride);
     }
-    // the hot path, twice (:218-219)
-    actual_state_controller->computeControl(fixed());
-    predicted_state_controller->computeControl();
+    // the hot path, twice (:218-219).  The two plans are independent, so both are enqueued before either is awaited:
+    // each fills a few percent of a B200 and they overlap on the device.
+    actual_state_controller->computeControlAsync(fixed());
+    predicted_state_controller->computeControlAsync();
+    actual_state_controller->waitControl();
+    predicted_state_controller->waitControl();
     if (use_feedback_gains) {
       actual_state_controller->computeFeedbackGains(state);
       predicted_state_controller->computeFeedbackGains(state);

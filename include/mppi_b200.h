@@ -139,6 +139,13 @@ int mppi_sample_noise(mppi_ctx *ctx, float *eps_out /* [B][rollout_count][T][2] 
 int mppi_compute_control(mppi_ctx *ctx, const float *state, float *U, const float *control_hist,
                          float *state_solution, float *control_solution, mppi_result *result);
 
+/* The two halves of mppi_compute_control: enqueue everything on the context's stream and return; wait and unpack.
+ * Contexts own independent streams, so the two controllers of the reference's control loop (actual-state and
+ * predicted-state, PI/run_control_loop.cuh:218-219), each of which fills a few percent of a B200, can run
+ * concurrently: async on both, then wait on both. */
+int mppi_compute_control_async(mppi_ctx *ctx, const float *state, const float *U, const float *control_hist);
+int mppi_compute_control_wait(mppi_ctx *ctx, float *U, float *state_solution, float *control_solution, mppi_result *result);
+
 /* Stage access for parity tests and multi-GPU plumbing (after a compute call): */
 int mppi_get_rollout_costs(mppi_ctx *ctx, float *costs /* [B][rollout_count] */);
 int mppi_get_rollout_crash(mppi_ctx *ctx, int *crash /* [B][rollout_count] */);
