@@ -42,6 +42,13 @@ constexpr int INBOX_STATE = 0;
 constexpr int INBOX_HIST = 7;
 constexpr int INBOX_U = 12;
 
+// Programmatic dependent launch (PDL, sm_90+): a kernel launched with the programmatic-stream-serialization attribute
+// may start while its predecessor is still running; pdl_wait() blocks until the predecessor grid has completed and its
+// writes are visible, pdl_trigger() lets the successor grid be scheduled early.  Both are no-ops for a normal launch.
+// Used to overlap each kernel's prologue (weights into registers, launch latency) with the tail of the previous one.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+
 // Order-preserving float <-> uint map so the minimum cost can be taken with integer atomics / redux.
 __device__ __forceinline__ unsigned int float_to_ordered(float f) {
   unsigned int b = __float_as_uint(f);

@@ -7,6 +7,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -36,6 +37,7 @@ struct mppi_ctx {
   int n_local = 0, r_begin = 0, B = 1, T = 0;
   cudaStream_t stream = nullptr;
   bool owns_stream = true;
+  bool pdl = true;  // programmatic dependent launch between the kernels of one pipeline (MPPI_NO_PDL=1 disables)
   // NCCL exchange (mppi_comm_init): communicator and the gathered records [num_ranks][B][shard_floats]
   void *nccl_comm = nullptr;
   int comm_rank = 0, comm_size = 1;
@@ -128,6 +130,17 @@ int resolve_variant(const mppi_ctx *c) {
   return v;
 }
 
+template <class K, class P>
+cudaError_t launch_pdl(mppi_ctx *c, K kernel, dim3 grid, int block, size_t smem, bool pdl, const P &params) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, params);
+}
+
 cudaError_t launch_rollout(mppi_ctx *c) {
   RolloutParams p{};
   p.inbox = c->d_inbox; p.du = c->d_du; p.costs = c->d_costs; p.crash = c->d_crash; p.baseline = c->d_baseline;
@@ -149,7 +162,7 @@ cudaError_t launch_rollout(mppi_ctx *c) {
     case MPPI_ROLLOUT_LANES8: return launch_rollout_nn32_lanes(p, c->stream, 8);
     case MPPI_ROLLOUT_LANES16: return launch_rollout_nn32_lanes(p, c->stream, 16);
     case MPPI_ROLLOUT_LANES32: return launch_rollout_nn32_lanes(p, c->stream, 32);
-    case MPPI_ROLLOUT_HALF16: return launch_rollout_nn32_half(p, c->stream);
+    case MPPI_ROLLOUT_HALF16: return launch_rollout_nn32_half(p, c->stream, c->pdl && !c->injected);
     default: return launch_rollout_nn32_r1(p, c->stream, small);
   }
 }
@@ -173,8 +186,7 @@ cudaError_t launch_weighting(mppi_ctx *c) {
   const int nrl = std::max(1, 256 / c->T);
   const size_t smem = (size_t)round_up(c->rows_per_blk, 4) * 4 + (size_t)nrl * c->T * 8;
   c->launches++;
-  weight_reduce_kernel<<<dim3(c->nblk, c->B), 256, smem, c->stream>>>(p);
-  return cudaGetLastError();
+  return launch_pdl(c, weight_reduce_kernel, dim3(c->nblk, c->B), 256, smem, c->pdl, p);
 }
 
 size_t finalize_smem(const mppi_ctx *c) {
@@ -194,8 +206,8 @@ cudaError_t launch_finalize(mppi_ctx *c, const float *gathered, int G, int last_
   p.negate_yaw = c->negate_yaw; p.last_iter = last_iter; p.feed_back = feed_back;
   p.baseline = c->d_baseline; p.call_counter = c->d_call_counter;
   c->launches++;
-  finalize_kernel<<<c->B, 256, finalize_smem(c), c->stream>>>(p);
-  return cudaGetLastError();
+  // after an NCCL exchange (gathered != own shard) the predecessor is not one of our kernels: plain launch
+  return launch_pdl(c, finalize_kernel, dim3(c->B), 256, finalize_smem(c), c->pdl && gathered == c->d_shard, p);
 }
 
 int check_ready(const mppi_ctx *c) {
@@ -291,6 +303,7 @@ int mppi_create(const mppi_config *cfg, mppi_ctx **out) {
   c->n_local = count; c->r_begin = cfg->rollout_begin; c->B = cfg->num_controllers; c->T = cfg->num_timesteps;
   c->dt = (float)(1.0 / cfg->hz);  // SRC/path_integral_main.cu:100
   c->gamma = cfg->gamma; c->seed = cfg->seed;
+  c->pdl = std::getenv("MPPI_NO_PDL") == nullptr;
   c->inbox_stride = round_up(INBOX_U + 2 * c->T, 4);
   c->outbox_stride = round_up(4 + 13 * c->T, 4);
   c->shard_floats = round_up(SHARD_HDR + 2 * c->T, 4);
@@ -825,9 +838,10 @@ int mppi_run_resident(mppi_ctx *c, int steps, int flush_l2, float *elapsed_ms, f
     if (per_step) CK(cudaEventRecord(c->step_events[4 * s], c->stream));
     for (int it = 0; it < c->cfg.num_iters; it++) {
       CK(launch_noise(c));
-      if (per_step && it == 0) CK(cudaEventRecord(c->step_events[4 * s + 2], c->stream));
+      // events inside the pipeline serialise it (no programmatic overlap): only when the kernel time is asked for
+      if (rollout_kernel_ms && it == 0) CK(cudaEventRecord(c->step_events[4 * s + 2], c->stream));
       CK(launch_rollout(c));
-      if (per_step && it == 0) CK(cudaEventRecord(c->step_events[4 * s + 3], c->stream));
+      if (rollout_kernel_ms && it == 0) CK(cudaEventRecord(c->step_events[4 * s + 3], c->stream));
       CK(launch_weighting(c));
       CK(launch_finalize(c, c->d_shard, 1, it == c->cfg.num_iters - 1, 1));
     }
@@ -841,8 +855,10 @@ int mppi_run_resident(mppi_ctx *c, int steps, int flush_l2, float *elapsed_ms, f
       float ms = 0.0f;
       CK(cudaEventElapsedTime(&ms, c->step_events[4 * s], c->step_events[4 * s + 1]));
       total += ms;
-      CK(cudaEventElapsedTime(&ms, c->step_events[4 * s + 2], c->step_events[4 * s + 3]));
-      roll += ms;
+      if (rollout_kernel_ms) {
+        CK(cudaEventElapsedTime(&ms, c->step_events[4 * s + 2], c->step_events[4 * s + 3]));
+        roll += ms;
+      }
     }
   }
   if (!flush_l2) CK(cudaEventElapsedTime(&total, c->ev0, c->ev1));

@@ -66,6 +66,8 @@ __global__ void __launch_bounds__(32, MINB) rollout_half_kernel(const __grid_con
   float roll = inbox[INBOX_STATE + 3], vx = inbox[INBOX_STATE + 4], vy = inbox[INBOX_STATE + 5], wz = inbox[INBOX_STATE + 6];
   const float2 *Ug = reinterpret_cast<const float2 *>(inbox + INBOX_U);
   float2 *row = reinterpret_cast<float2 *>(p.du) + (size_t)gro * T;
+  pdl_trigger();
+  pdl_wait();  // everything above reads parameters and the inbox only; the noise comes from the sampler kernel
   const int rg = p.r_begin + lr;  // the GLOBAL rollout index drives the bookkeeping (R2)
   const bool noise_free = (rg == 0), pure_noise = (rg >= p.pure_noise_from);
   bool crash_in = false;
@@ -174,7 +176,7 @@ __global__ void __launch_bounds__(32, MINB) rollout_half_kernel(const __grid_con
 
 }  // namespace
 
-cudaError_t launch_rollout_nn32_half(const RolloutParams &p, cudaStream_t st) {
+cudaError_t launch_rollout_nn32_half(const RolloutParams &p, cudaStream_t st, bool pdl) {
   const long long total = (long long)p.B * p.n_local;  // multiple of 64
   const size_t smem = (128 + 2 * (size_t)p.T) * sizeof(float);
   const bool roomy = total / 2 <= 148LL * 12;  // every CTA resident at once with the 166-register build
@@ -183,9 +185,13 @@ cudaError_t launch_rollout_nn32_half(const RolloutParams &p, cudaStream_t st) {
                           : cudaFuncSetAttribute(rollout_half_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  if (roomy) rollout_half_kernel<12><<<(unsigned)(total / 2), 32, smem, st>>>(p);
-  else rollout_half_kernel<16><<<(unsigned)(total / 2), 32, smem, st>>>(p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(total / 2)); cfg.blockDim = dim3(32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return roomy ? cudaLaunchKernelEx(&cfg, rollout_half_kernel<12>, p) : cudaLaunchKernelEx(&cfg, rollout_half_kernel<16>, p);
 }
 
 }  // namespace mppi

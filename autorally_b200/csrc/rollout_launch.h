@@ -10,7 +10,8 @@ cudaError_t launch_rollout_nn32_r1(const RolloutParams &p, cudaStream_t st, bool
 cudaError_t launch_rollout_nn32_r2(const RolloutParams &p, cudaStream_t st, bool small);
 cudaError_t launch_rollout_nn32_split8(const RolloutParams &p, cudaStream_t st);
 cudaError_t launch_rollout_nn32_lanes(const RolloutParams &p, cudaStream_t st, int lanes);
-cudaError_t launch_rollout_nn32_half(const RolloutParams &p, cudaStream_t st);
+// pdl: launch with programmatic stream serialization (the kernel overlaps its prologue with its predecessor's tail)
+cudaError_t launch_rollout_nn32_half(const RolloutParams &p, cudaStream_t st, bool pdl);
 cudaError_t launch_rollout_nn64_r1(const RolloutParams &p, cudaStream_t st, bool small);
 cudaError_t launch_rollout_bf(const RolloutParams &p, cudaStream_t st, bool small);
 

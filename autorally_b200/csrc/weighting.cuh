@@ -43,6 +43,7 @@ __device__ __forceinline__ float2 box_muller(uint32_t xa, uint32_t xb) {
 __global__ void __launch_bounds__(256) sample_noise_kernel(float *__restrict__ du, int n_local, int r_begin, int T,
                                                             int B, uint32_t seed_lo, uint32_t seed_hi,
                                                             const uint32_t *__restrict__ call_ptr) {
+  pdl_trigger();  // the rollout kernel may start fetching its weights now
   const uint32_t call = *call_ptr;
   const int Q = (T + 1) >> 1;
   const long long total = (long long)B * n_local * Q;
@@ -92,6 +93,8 @@ __global__ void __launch_bounds__(256) weight_reduce_kernel(const __grid_constan
   __shared__ float red[2][8];
   __shared__ bool is_last;
   const int b = blockIdx.y, blk = blockIdx.x, tid = threadIdx.x;
+  pdl_trigger();
+  pdl_wait();  // rollout costs, sampled controls and the baseline come from the rollout kernel
   const int r0 = blk * p.rows_per_blk;
   const int nrows = min(p.rows_per_blk, p.n_local - r0);
   const float base = ordered_to_float(p.baseline[b]);
@@ -250,7 +253,9 @@ __device__ __forceinline__ void nominal_traj_nn32(const WarpMlp32 &net, const fl
     sincosf(r_yaw, &sn, &cs);
     const float d0 = fmaf(cs, r_vx, -__fmul_rn(sn, r_vy)), d1 = fmaf(sn, r_vx, __fmul_rn(cs, r_vy));
     float myx = 0.0f, myy = 0.0f;
-    for (int j = 0; j < nb; j++) {
+    // fully unrolled so the 64 shuffles are in flight together; lanes beyond the horizon hold zeros (exact no-ops)
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
       if (lane == j) { myx = x; myy = y; }
       x = fmaf(__shfl_sync(full, d0, j), dt, x);
       y = fmaf(__shfl_sync(full, d1, j), dt, y);
@@ -281,6 +286,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ F
   // warp 0 fetches its slices of the network while the other warps combine the shard records
   WarpMlp32 net;
   if (p.is_nn32 && p.last_iter && tid < 32) net.load(p.theta_t, tid);
+  pdl_wait();  // the shard records come from the weighting kernel (or the exchange)
 
   if (tid == 0) {
     float base = p.gathered[((size_t)0 * p.B + b) * p.shard_floats];
