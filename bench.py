@@ -356,12 +356,12 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")
     if os.path.exists(tpath):   # dram__bytes_read.sum + dram__bytes_write.sum of the rollout kernel, one ncu --set full capture
         t = json.load(open(tpath))["configs"]
-        k = t["1920"]["rollout_lanes_kernel"]
+        k = t["1920"].get("rollout_half_kernel") or next(iter(t["1920"].values()))
         traffic, traffic_src = k["dram_read_bytes"] + k["dram_write_bytes"], "profiles/ncu_traffic_r01.json (cold-cache ncu replay)"
     achieved = FLOP_PER_ROLLOUT_STEP_NN * N_ROLLOUTS * T_STEPS / (rollout_ms * 1e-3) / 1e12
     roofline = {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
                 "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": 16.0 * N_ROLLOUTS * T_STEPS,
-                "kernel": "rollout_lanes_kernel<32>" if ctx.resolved_variant() == 7 else "rollout kernel (variant %d)" % ctx.resolved_variant(),
+                "kernel": "rollout_half_kernel" if ctx.resolved_variant() == 9 else "rollout kernel (variant %d)" % ctx.resolved_variant(),
                 "kernel_ms": rollout_ms,
                 "note": "FP32 FFMA issue bound (CUDA cores; neither HBM nor tensor); peak = FFMA microbenchmark measured in this run; "
                         "1920 rollouts occupy <2% of the machine, see 'large' for the filled-GPU fraction"}
