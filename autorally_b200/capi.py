@@ -37,6 +37,7 @@ EXPORTED_SYMBOLS = [
     "mppi_shard_begin_async", "mppi_shard_finish_async", "mppi_shard_result", "mppi_set_stream",
     "mppi_comm_unique_id", "mppi_comm_init", "mppi_comm_destroy", "mppi_compute_control_sharded",
     "mppi_run_resident_sharded", "mppi_compute_control_async", "mppi_compute_control_wait",
+    "mppi_bench_compute_control",
 ]
 
 
@@ -212,6 +213,16 @@ class MppiContext:
         res = (MppiResult * B)()
         self._ck(self.lib.mppi_compute_control_wait(self._ctx, _fp(U), _fp(ss), _fp(cs), res), "mppi_compute_control_wait")
         return self._result(U, ss, cs, res)
+
+    def bench_compute_control(self, state, U, hist=None, reps=100):
+        """Per-call host latencies (ms) of `reps` C-side mppi_compute_control calls; returns (latencies, final U)."""
+        B, T = self.B, self.T
+        state = _f32(state).reshape(B, 7)
+        U = _f32(U).reshape(B, T, 2).copy()
+        hist = _f32(hist if hist is not None else np.zeros((B, 4))).reshape(B, 4)
+        lat = np.zeros(reps, np.float32)
+        self._ck(self.lib.mppi_bench_compute_control(self._ctx, _fp(state), _fp(U), _fp(hist), int(reps), _fp(lat)), "mppi_bench_compute_control")
+        return lat, U
 
     def rollout_costs(self):
         c = np.zeros((self.B, self.n_local), np.float32)

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -64,6 +65,9 @@ struct mppi_ctx {
   // buffers
   int inbox_stride = 0, outbox_stride = 0, shard_floats = 0;
   float *d_inbox = nullptr, *d_outbox = nullptr, *h_inbox = nullptr, *h_outbox = nullptr;
+  // device aliases of the pinned host inbox / outbox (zero-copy: the sampler pulls the inputs, finalize pushes the results)
+  float *h_inbox_dev = nullptr, *h_outbox_dev = nullptr;
+  bool zero_copy = false;
   float *d_du = nullptr, *d_costs = nullptr;
   unsigned char *d_crash = nullptr;
   unsigned int *d_baseline = nullptr, *d_done = nullptr;
@@ -167,13 +171,15 @@ cudaError_t launch_rollout(mppi_ctx *c) {
   }
 }
 
-cudaError_t launch_noise(mppi_ctx *c) {
+cudaError_t launch_noise(mppi_ctx *c, bool pull_inbox = false) {
   const long long total = (long long)c->B * c->n_local * ((c->T + 1) / 2);
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   c->launches++;
-  sample_noise_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(c->d_du, c->n_local, c->r_begin, c->T, c->B, (uint32_t)c->seed,
-                                                              (uint32_t)(c->seed >> 32), c->d_call_counter);
+  sample_noise_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(
+      c->d_du, c->n_local, c->r_begin, c->T, c->B, (uint32_t)c->seed, (uint32_t)(c->seed >> 32), c->d_call_counter,
+      pull_inbox ? reinterpret_cast<const float4 *>(c->h_inbox_dev) : nullptr, reinterpret_cast<float4 *>(c->d_inbox),
+      c->B * c->inbox_stride / 4);
   return cudaGetLastError();
 }
 
@@ -194,9 +200,9 @@ size_t finalize_smem(const mppi_ctx *c) {
   return (4 * (size_t)c->T + 2 * FIN_MAX_WIDTH + nparams) * sizeof(float);
 }
 
-cudaError_t launch_finalize(mppi_ctx *c, const float *gathered, int G, int last_iter, int feed_back) {
+cudaError_t launch_finalize(mppi_ctx *c, const float *gathered, int G, int last_iter, int feed_back, bool push_outbox = false) {
   FinalizeParams p{};
-  p.gathered = gathered; p.inbox = c->d_inbox; p.outbox = c->d_outbox; p.theta_t = c->d_theta_t;
+  p.gathered = gathered; p.inbox = c->d_inbox; p.outbox = push_outbox ? c->h_outbox_dev : c->d_outbox; p.theta_t = c->d_theta_t;
   p.net_structure = c->d_net_structure;
   p.num_layers = c->cfg.dynamics == MPPI_DYNAMICS_BF ? 0 : (int)c->net_structure.size();
   p.is_nn32 = (c->cfg.dynamics == MPPI_DYNAMICS_NN && c->net_kind == 32) ? 1 : 0;
@@ -228,13 +234,13 @@ void stage_inbox(mppi_ctx *c, const float *state, const float *U, const float *h
 }
 
 // noise (or injected noise upload) -> baseline reset -> rollouts -> local weighting partials
-int run_front(mppi_ctx *c, int iter) {
+int run_front(mppi_ctx *c, int iter, bool pull_inbox = false) {
   if (c->injected) {
     const size_t per_iter = (size_t)c->B * c->n_local * c->T * 2;
     if (c->injected_noise.size() < per_iter * (size_t)(iter + 1)) return MPPI_ERR_INVALID_ARG;
     CK(cudaMemcpyAsync(c->d_du, c->injected_noise.data() + per_iter * iter, per_iter * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   } else {
-    CK(launch_noise(c));
+    CK(launch_noise(c, pull_inbox));
   }
   CK(launch_rollout(c));   // the baseline slots were re-armed by the previous finalize_kernel
   CK(launch_weighting(c));
@@ -323,8 +329,11 @@ int mppi_create(const mppi_config *cfg, mppi_ctx **out) {
   const size_t B = c->B, n = c->n_local, T = c->T;
   CKF(cudaMalloc(&c->d_inbox, B * c->inbox_stride * sizeof(float)));
   CKF(cudaMalloc(&c->d_outbox, B * c->outbox_stride * sizeof(float)));
-  CKF(cudaMallocHost(&c->h_inbox, B * c->inbox_stride * sizeof(float)));
-  CKF(cudaMallocHost(&c->h_outbox, B * c->outbox_stride * sizeof(float)));
+  CKF(cudaHostAlloc(&c->h_inbox, B * c->inbox_stride * sizeof(float), cudaHostAllocMapped));
+  CKF(cudaHostAlloc(&c->h_outbox, B * c->outbox_stride * sizeof(float), cudaHostAllocMapped));
+  CKF(cudaHostGetDevicePointer(&c->h_inbox_dev, c->h_inbox, 0));
+  CKF(cudaHostGetDevicePointer(&c->h_outbox_dev, c->h_outbox, 0));
+  c->zero_copy = B * c->outbox_stride * sizeof(float) <= 64 * 1024 && std::getenv("MPPI_NO_ZERO_COPY") == nullptr;
   CKF(cudaMalloc(&c->d_du, B * n * T * 2 * sizeof(float)));
   CKF(cudaMalloc(&c->d_costs, B * n * sizeof(float)));
   CKF(cudaMalloc(&c->d_crash, B * n));
@@ -540,13 +549,17 @@ int mppi_sample_noise(mppi_ctx *c, float *eps_out) {
 }
 
 static int enqueue_compute(mppi_ctx *c) {
-  CK(cudaMemcpyAsync(c->d_inbox, c->h_inbox, (size_t)c->B * c->inbox_stride * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  // Zero-copy for the small per-call payloads (state / U / history in, results out): the sampler kernel pulls the inbox
+  // from mapped pinned memory and finalize_kernel writes the outbox into it, which removes the two copy nodes of the
+  // graph (the same bytes still cross PCIe).  Injected-noise runs and large batches use explicit copies.
+  const bool zc = c->zero_copy && !c->injected;
+  if (!zc) CK(cudaMemcpyAsync(c->d_inbox, c->h_inbox, (size_t)c->B * c->inbox_stride * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   for (int it = 0; it < c->cfg.num_iters; it++) {
-    int rc = run_front(c, it);
+    int rc = run_front(c, it, zc && it == 0);
     if (rc) return rc;
-    CK(launch_finalize(c, c->d_shard, 1, it == c->cfg.num_iters - 1, 0));
+    CK(launch_finalize(c, c->d_shard, 1, it == c->cfg.num_iters - 1, 0, zc));
   }
-  CK(cudaMemcpyAsync(c->h_outbox, c->d_outbox, (size_t)c->B * c->outbox_stride * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  if (!zc) CK(cudaMemcpyAsync(c->h_outbox, c->d_outbox, (size_t)c->B * c->outbox_stride * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   return MPPI_OK;
 }
 
@@ -588,6 +601,16 @@ int mppi_compute_control_async(mppi_ctx *c, const float *state, const float *U, 
 int mppi_compute_control_wait(mppi_ctx *c, float *U, float *ss, float *cs, mppi_result *res) {
   if (!c) return MPPI_ERR_INVALID_ARG;
   CK(cudaSetDevice(c->device));
+  // A controller call lasts ~0.1 ms: poll the stream for a short while before falling back to a blocking wait, whose
+  // wake-up latency would otherwise be a tenth of the whole call.
+  {
+    const auto t0 = std::chrono::steady_clock::now();
+    cudaError_t q;
+    while ((q = cudaStreamQuery(c->stream)) == cudaErrorNotReady) {
+      if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(400)) break;
+    }
+    if (q != cudaSuccess && q != cudaErrorNotReady) return (int)q;
+  }
   CK(cudaStreamSynchronize(c->stream));
   unpack_outbox(c, U, ss, cs, res);
   return MPPI_OK;
@@ -597,6 +620,22 @@ int mppi_compute_control(mppi_ctx *c, const float *state, float *U, const float 
   int rc = mppi_compute_control_async(c, state, U, hist);
   if (rc) return rc;
   return mppi_compute_control_wait(c, U, ss, cs, res);
+}
+
+// Host-observed latency of `reps` consecutive mppi_compute_control calls made from C (what a C++ control loop sees;
+// the ctypes binding adds its own argument marshalling on top).  U is fed back from call to call.
+int mppi_bench_compute_control(mppi_ctx *c, const float *state, float *U, const float *hist, int reps, float *latency_ms) {
+  if (!c || !state || !U || !latency_ms || reps < 1) return MPPI_ERR_INVALID_ARG;
+  std::vector<float> ss((size_t)c->B * c->T * S_DIM), cs((size_t)c->B * c->T * 2);
+  std::vector<mppi_result> res(c->B);
+  for (int r = 0; r < reps; r++) {
+    const auto t0 = std::chrono::steady_clock::now();
+    const int rc = mppi_compute_control(c, state, U, hist, ss.data(), cs.data(), res.data());
+    const auto t1 = std::chrono::steady_clock::now();
+    if (rc) return rc;
+    latency_ms[r] = std::chrono::duration<float, std::milli>(t1 - t0).count();
+  }
+  return MPPI_OK;
 }
 
 int mppi_get_rollout_costs(mppi_ctx *c, float *costs) {

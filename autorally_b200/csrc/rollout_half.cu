@@ -62,12 +62,12 @@ __global__ void __launch_bounds__(32, MINB) rollout_half_kernel(const __grid_con
   for (int m = 0; m < 4; m++) w3[m] = make_float2(th[kW3 + (8 * q + 2 * m) * 4 + jo], th[kW3 + (8 * q + 2 * m + 1) * 4 + jo]);
   const float b3 = th[kB3 + jo];
 
-  float xcur = inbox[INBOX_STATE + 0], ycur = inbox[INBOX_STATE + 1], yaw = inbox[INBOX_STATE + 2];
-  float roll = inbox[INBOX_STATE + 3], vx = inbox[INBOX_STATE + 4], vy = inbox[INBOX_STATE + 5], wz = inbox[INBOX_STATE + 6];
   const float2 *Ug = reinterpret_cast<const float2 *>(inbox + INBOX_U);
   float2 *row = reinterpret_cast<float2 *>(p.du) + (size_t)gro * T;
   pdl_trigger();
-  pdl_wait();  // everything above reads parameters and the inbox only; the noise comes from the sampler kernel
+  pdl_wait();  // everything above reads model parameters only; noise and inbox come from the sampler kernel
+  float xcur = inbox[INBOX_STATE + 0], ycur = inbox[INBOX_STATE + 1], yaw = inbox[INBOX_STATE + 2];
+  float roll = inbox[INBOX_STATE + 3], vx = inbox[INBOX_STATE + 4], vy = inbox[INBOX_STATE + 5], wz = inbox[INBOX_STATE + 6];
   const int rg = p.r_begin + lr;  // the GLOBAL rollout index drives the bookkeeping (R2)
   const bool noise_free = (rg == 0), pure_noise = (rg >= p.pure_noise_from);
   bool crash_in = false;

@@ -40,10 +40,18 @@ __device__ __forceinline__ float2 box_muller(uint32_t xa, uint32_t xb) {
 
 // `call_ptr` is the device-resident compute-call counter (advanced by finalize_kernel), so a captured
 // CUDA graph replays with a fresh Philox offset every launch.
+//
+// Side job (zero-copy inbox): when inbox_src != nullptr, CTA 0 copies the call's inputs (state, history, U; 848 B at
+// T = 100) from mapped pinned host memory into the device inbox, which replaces a separate H2D copy node in front of
+// the pipeline; the rollout kernel reads the inbox only after this grid has completed.
 __global__ void __launch_bounds__(256) sample_noise_kernel(float *__restrict__ du, int n_local, int r_begin, int T,
                                                             int B, uint32_t seed_lo, uint32_t seed_hi,
-                                                            const uint32_t *__restrict__ call_ptr) {
+                                                            const uint32_t *__restrict__ call_ptr,
+                                                            const float4 *__restrict__ inbox_src, float4 *__restrict__ inbox_dst,
+                                                            int inbox_float4s) {
   pdl_trigger();  // the rollout kernel may start fetching its weights now
+  if (inbox_src != nullptr && blockIdx.x == 0)
+    for (int i = threadIdx.x; i < inbox_float4s; i += blockDim.x) inbox_dst[i] = inbox_src[i];
   const uint32_t call = *call_ptr;
   const int Q = (T + 1) >> 1;
   const long long total = (long long)B * n_local * Q;

@@ -146,6 +146,11 @@ int mppi_compute_control(mppi_ctx *ctx, const float *state, float *U, const floa
 int mppi_compute_control_async(mppi_ctx *ctx, const float *state, const float *U, const float *control_hist);
 int mppi_compute_control_wait(mppi_ctx *ctx, float *U, float *state_solution, float *control_solution, mppi_result *result);
 
+/* Measurement helper: `reps` consecutive mppi_compute_control calls made from C with the given host buffers (U fed back
+ * from call to call); latency_ms[reps] receives each call's host-observed duration (steady clock). */
+int mppi_bench_compute_control(mppi_ctx *ctx, const float *state, float *U, const float *control_hist, int reps,
+                               float *latency_ms);
+
 /* Stage access for parity tests and multi-GPU plumbing (after a compute call): */
 int mppi_get_rollout_costs(mppi_ctx *ctx, float *costs /* [B][rollout_count] */);
 int mppi_get_rollout_crash(mppi_ctx *ctx, int *crash /* [B][rollout_count] */);
