@@ -237,3 +237,29 @@ def test_resident_stepping_runs_and_counts_launches(models, costmap):
         ms, rk = ctx.run_resident(5, time_rollout=True)
         assert ms > 0 and 0 < rk <= ms
         assert ctx.last_launch_count() == 5 * 4
+
+
+def test_launch_paths_are_bitwise_equivalent(models, costmap, monkeypatch):
+    """The production call path (CUDA graph, programmatic dependent launch, zero-copy inbox / outbox) and the plain one
+    (explicit copies, fully serialised launches) must produce identical bits for the same Philox seed and call counter."""
+    cp = cost_params_for(costmap)
+    state, U = top_state(4.0), straight_controls(100)
+    hist = np.array([0.1, 0.3, 0.11, 0.32], np.float32)
+    results = []
+    for no_pdl, no_zc in [(False, False), (True, False), (False, True), (True, True)]:
+        for name, on in (("MPPI_NO_PDL", no_pdl), ("MPPI_NO_ZERO_COPY", no_zc)):
+            if on:
+                monkeypatch.setenv(name, "1")
+            else:
+                monkeypatch.delenv(name, raising=False)
+        with make_context("nn", models, costmap, cp, 1920, seed=4242) as ctx:
+            ctx.seed(4242, 7)
+            a = ctx.compute_control(state, U, hist)
+            b = ctx.compute_control(state, a["U"], hist)   # second call: graph replay, call counter 8
+            results.append((a, b, ctx.rollout_costs()))
+    for a, b, c in results[1:]:
+        for k in ("U", "state_solution", "control_solution", "baseline", "normalizer", "trajectory_cost"):
+            np.testing.assert_array_equal(a[k], results[0][0][k])
+            np.testing.assert_array_equal(b[k], results[0][1][k])
+        np.testing.assert_array_equal(c, results[0][2])
+    assert not np.array_equal(results[0][0]["U"], results[0][1]["U"])  # fresh noise on the second call

@@ -160,3 +160,30 @@ def test_reference_latency_is_reported(models, costmap):
         ms = rc.time_compute_control(default_state(5.0), reps=10)
     print("reference computeControl (1920x100, sm_100a build): %.3f ms/call" % ms)
     assert ms > 0
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_randomized_scenarios_three_way(models, costmap, seed):
+    """Random poses along the track (random lateral offset, heading error, speed, slip), random smooth nominal controls,
+    random cost parameters and exploration: the reference's kernels, the CUDA path and the oracle on the same draws."""
+    rng = np.random.default_rng(1000 + seed)
+    ang = rng.uniform(0, 2 * np.pi)
+    a, b = 20.0, 12.0
+    off = rng.uniform(-0.8, 0.8)
+    x, y = (a + off) * np.cos(ang), (b + off) * np.sin(ang)
+    yaw = np.arctan2(b * np.cos(ang), -a * np.sin(ang)) + rng.uniform(-0.3, 0.3)
+    state = np.array([x, y, yaw, rng.uniform(-0.05, 0.05), rng.uniform(0.0, 9.0), rng.uniform(-0.5, 0.5), rng.uniform(-0.5, 0.5)], np.float32)
+    t = np.arange(100)
+    U = np.stack([rng.uniform(-0.3, 0.3) + 0.1 * np.sin(t / rng.uniform(5, 30)),
+                  rng.uniform(0.0, 0.6) + 0.1 * np.cos(t / rng.uniform(5, 30))], 1).astype(np.float32)
+    over = dict(desired_speed=float(rng.uniform(3, 10)), speed_coeff=float(rng.uniform(1, 8)), track_coeff=float(rng.uniform(50, 400)),
+                max_slip_ang=float(rng.uniform(0.5, 1.5)), slip_penalty=float(rng.uniform(1, 20)), track_slop=float(rng.choice([0.0, 0.1])),
+                steering_coeff=float(rng.choice([0.0, 0.3])), throttle_coeff=float(rng.choice([0.0, 0.2])),
+                boundary_threshold=float(rng.uniform(0.5, 0.9)), discount=float(rng.uniform(0.0, 0.3)), l1_cost=bool(rng.integers(2)))
+    cp = cost_params_for(costmap, **over)
+    gamma = float(rng.choice([0.15, 0.05, 0.5]))
+    want = reference_run(ref.REF_NN_1920, models["autorally_nnet_theta"], costmap, cp, state, U, gamma=gamma)
+    got = cuda_run("nn", models, costmap, cp, 1920, state, U, want["eps"], gamma=gamma)
+    compare(got, want, 100, "cuda vs reference (seed %d)" % seed)
+    o = make_oracle("nn", models, costmap, cp).compute_control(state, U, HIST, NU, want["eps"], gamma=gamma, threads=8)
+    compare(o, want, 100, "oracle vs reference (seed %d)" % seed)
