@@ -32,7 +32,7 @@ class SimPlant {
   void getObstacles(std::vector<int> &, std::vector<float> &) {}
   bool hasNewCostmap() const { return false; }
   void getCostmap(std::vector<int> &, std::vector<float> &) {}
-  bool hasNewModel() const { return has_model_; }
+  bool hasNewModel() const { return has_model_ && (int)controller_used_.size() >= model_at_iteration_; }
   void getModel(std::vector<int> &description, std::vector<float> &data) { description = model_description_; data = model_data_; has_model_ = false; }
   template <class GAINS>
   void setSolution(const std::vector<float> &state_seq, const std::vector<float> &control_seq, const GAINS &, double ts,
@@ -48,7 +48,11 @@ class SimPlant {
 
   // ---- test / driver side ----
   void pushDynRcfg(const PathIntegralParamsConfig &c) { dcfg_ = c; has_dcfg_ = true; }
-  void pushModel(const std::vector<int> &description, const std::vector<float> &data) { model_description_ = description; model_data_ = data; has_model_ = true; }
+  /// Queue a model for hot swap (the /model_updater/model topic of the reference, SRC/autorally_plant.cpp:262-301);
+  /// it becomes visible to the loop once `at_iteration` solutions have been handed over.
+  void pushModel(const std::vector<int> &description, const std::vector<float> &data, int at_iteration = 0) {
+    model_description_ = description; model_data_ = data; has_model_ = true; model_at_iteration_ = at_iteration;
+  }
   const std::vector<float> &executedStates() const { return executed_states_; }      // [iterations][7]
   const std::vector<float> &executedControls() const { return executed_controls_; }  // [iterations][2]
   const std::vector<int> &controllerUsed() const { return controller_used_; }
@@ -58,6 +62,7 @@ class SimPlant {
   FullState full_state_;
   double last_pose_time_ = 0.0, solution_ts_ = 0.0, avg_loop_ = 0, avg_tick_ = 0, avg_sleep_ = 0;
   bool has_dcfg_ = false, has_model_ = false;
+  int model_at_iteration_ = 0;
   PathIntegralParamsConfig dcfg_;
   std::vector<int> model_description_, controller_used_;
   std::vector<float> model_data_, state_seq_, control_seq_, executed_states_, executed_controls_;

@@ -3,7 +3,9 @@
 // runControlLoop in debug mode (the host model is the plant) for `profiler_max_iter` iterations.  Writes the executed
 // state / control log for the closed-loop test (tests/test_control_loop.py).
 //
-// usage: control_loop_driver <nn|bf> <launch_file> <out.npz> <iterations> <x> <y> <heading> [double_step]
+// usage: control_loop_driver <nn|bf> <launch_file> <out.npz> <iterations> <x> <y> <heading> [double_step [swap.npz swap_iteration]]
+//   swap.npz: arrays `description` (int32 layer widths) and `data` (float32, all weights then all biases): the flattened
+//   /model_updater/model message, handed to the loop after `swap_iteration` iterations (model hot swap).
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -49,6 +51,15 @@ int run(int argc, char **argv) {
   Controller *actual = new Controller(model, costs, exploration_std, init_u, hz, T, stride, gamma, num_iters);
   Controller *predicted = new Controller(model, costs, exploration_std, init_u, hz, T, stride, gamma, num_iters);
   SimPlant robot((float)atof(argv[5]), (float)atof(argv[6]), (float)atof(argv[7]));
+  if (argc > 10) {
+    npz::Archive swap = npz::load(argv[9]);
+    const npz::Array &d = swap.at("description"), &v = swap.at("data");
+    std::vector<int> description(d.num_vals());
+    std::vector<float> data(v.num_vals());
+    for (size_t i = 0; i < description.size(); i++) description[i] = (int)d.at(i);
+    for (size_t i = 0; i < data.size(); i++) data[i] = (float)v.at(i);
+    robot.pushModel(description, data, atoi(argv[10]));
+  }
   std::atomic<bool> is_alive(true);
   runControlLoop<Controller, SimPlant>(predicted, actual, &robot, &params, &is_alive);
 

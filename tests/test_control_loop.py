@@ -14,12 +14,18 @@ from tests.test_host_cpp import LIB, write_inputs
 pytestmark = pytest.mark.gpu
 
 
-def run_loop(tmp_path, models, costmap, kind, iterations, pose, double_step=0):
+def run_loop(tmp_path, models, costmap, kind, iterations, pose, double_step=0, swap=None):
     exe = os.path.join(LIB, "control_loop_driver")
     assert os.path.exists(exe), "run __graft_entry__.build() first"
     launch, env = write_inputs(tmp_path, models, costmap, kind)
     out = tmp_path / "loop.npz"
-    subprocess.check_call([exe, kind, launch, str(out), str(iterations)] + [repr(float(v)) for v in pose] + [str(double_step)], env=env)
+    extra = []
+    if swap is not None:  # (theta, structure, iteration): hot swap through the flattened update-model message
+        from autorally_b200.model_io import flatten_for_update_model
+        description, data = flatten_for_update_model(swap[0], swap[1])
+        np.savez(tmp_path / "swap.npz", description=description.astype(np.int32), data=data.astype(np.float32))
+        extra = [str(tmp_path / "swap.npz"), str(swap[2])]
+    subprocess.check_call([exe, kind, launch, str(out), str(iterations)] + [repr(float(v)) for v in pose] + [str(double_step)] + extra, env=env)
     return np.load(out)
 
 
@@ -64,3 +70,16 @@ def test_reference_debug_double_step_quirk_is_optional(tmp_path, models, costmap
     da = np.abs(np.diff(a[:, 0])).sum() + np.abs(np.diff(a[:, 1])).sum()
     db = np.abs(np.diff(b[:, 0])).sum() + np.abs(np.diff(b[:, 1])).sum()
     assert db > 1.5 * da
+
+
+def test_model_hot_swap_through_the_update_model_message(tmp_path, models, costmap):
+    """updateModel(description, data) (PI/neural_net_model.cu:152-180; all weights then all biases) takes effect on the
+    next computeControl: swapping in the SAME weights changes nothing, swapping in another model changes the drive from
+    the swap iteration on and only from there (the Philox stream is deterministic)."""
+    pose, n, k = (0.0, 12.0, np.pi), 160, 80
+    base = run_loop(tmp_path, models, costmap, "nn", n, pose)["states"]
+    same = run_loop(tmp_path, models, costmap, "nn", n, pose, swap=(models["autorally_nnet_theta"], models["autorally_nnet_structure"], k))["states"]
+    np.testing.assert_array_equal(same, base)
+    other = run_loop(tmp_path, models, costmap, "nn", n, pose, swap=(models["gazebo_nnet_theta"], models["gazebo_nnet_structure"], k))["states"]
+    np.testing.assert_array_equal(other[:k + 1], base[:k + 1])
+    assert np.abs(other[k + 5:] - base[k + 5:]).max() > 1e-3
