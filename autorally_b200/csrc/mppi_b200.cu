@@ -213,7 +213,8 @@ cudaError_t launch_finalize(mppi_ctx *c, const float *gathered, int G, int last_
   p.baseline = c->d_baseline; p.call_counter = c->d_call_counter;
   c->launches++;
   // after an NCCL exchange (gathered != own shard) the predecessor is not one of our kernels: plain launch
-  return launch_pdl(c, finalize_kernel, dim3(c->B), 256, finalize_smem(c), c->pdl && gathered == c->d_shard, p);
+  // many batched controllers: small CTAs, so that more of the single-warp nominal trajectories are resident per SM
+  return launch_pdl(c, finalize_kernel, dim3(c->B), c->B >= 64 ? 64 : 256, finalize_smem(c), c->pdl && gathered == c->d_shard, p);
 }
 
 int check_ready(const mppi_ctx *c) {

@@ -55,6 +55,26 @@ __global__ void __launch_bounds__(256) sample_noise_kernel(float *__restrict__ d
   const uint32_t call = *call_ptr;
   const int Q = (T + 1) >> 1;
   const long long total = (long long)B * n_local * Q;
+  // 32-bit index arithmetic whenever it fits (it does up to 2^31 float4 = 32 GiB of noise): the 64-bit division and
+  // modulo by run-time values were most of this kernel's instructions (166 per float4 at 1M rollouts)
+  if (total < (1LL << 31)) {
+    const unsigned utotal = (unsigned)total, uQ = (unsigned)Q, un = (unsigned)n_local, stride = gridDim.x * blockDim.x;
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < utotal; idx += stride) {
+      const unsigned g = idx / uQ, q = idx - g * uQ;
+      const unsigned b = (B == 1) ? 0u : g / un, lr = g - b * un;
+      uint32_t x[4];
+      philox4x32_10(q, (uint32_t)r_begin + lr, call, b, seed_lo, seed_hi, x);
+      const float2 z0 = box_muller(x[0], x[1]), z1 = box_muller(x[2], x[3]);
+      float *dst = du + ((size_t)g * T + 2 * q) * C_DIM;
+      if ((T & 1) == 0) {
+        *reinterpret_cast<float4 *>(dst) = make_float4(z0.x, z0.y, z1.x, z1.y);
+      } else {
+        dst[0] = z0.x; dst[1] = z0.y;
+        if (2 * q + 1 < (unsigned)T) { dst[2] = z1.x; dst[3] = z1.y; }
+      }
+    }
+    return;
+  }
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int q = (int)(idx % Q);
     const long long g = idx / Q;
@@ -275,14 +295,14 @@ __device__ __forceinline__ void nominal_traj_nn32(const WarpMlp32 &net, const fl
   }
 }
 
-// grid B, block 256.  Combines the G shard records (log-sum-exp rescale),
+// grid B, block 256 (64 when many controllers are batched: only warp 0 does the long part).  Combines the G shard records (log-sum-exp rescale),
 // U_new = W / Z (control update :663-667), Savitzky-Golay (:468-499), then warp 0 integrates the
 // nominal trajectory with the host-twin arithmetic (separate multiply and add, precise tanhf/sinf/cosf).
 __global__ void bump_counter_kernel(uint32_t *counter) { *counter += 1u; }
 
 __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ FinalizeParams p) {
   extern __shared__ float fsm[];
-  const int T = p.T, tid = threadIdx.x, b = blockIdx.x;
+  const int T = p.T, tid = threadIdx.x, b = blockIdx.x, nthr = blockDim.x;
   float *Unew = fsm;                 // [2T]
   float *Usm = Unew + 2 * T;         // [2T]
   float *act = Usm + 2 * T;          // [2][FIN_MAX_WIDTH]
@@ -311,7 +331,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ F
   }
   __syncthreads();
   const float Z = hdr[1];
-  for (int k = tid; k < 2 * T; k += 256) {
+  for (int k = tid; k < 2 * T; k += nthr) {
     float wsum = 0.0f;
     for (int g = 0; g < p.G; g++) wsum = fmaf(scale[g], p.gathered[((size_t)g * p.B + b) * p.shard_floats + SHARD_HDR + k], wsum);
     Unew[k] = wsum / Z;
@@ -322,14 +342,14 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ F
     if (b == 0) *p.call_counter += 1u;
   }
   __syncthreads();
-  for (int k = tid; k < 2 * T; k += 256) outbox[4 + 2 * T + k] = Unew[k];
+  for (int k = tid; k < 2 * T; k += nthr) outbox[4 + 2 * T + k] = Unew[k];
   if (!p.last_iter) {
-    for (int k = tid; k < 2 * T; k += 256) inbox[INBOX_U + k] = Unew[k];
+    for (int k = tid; k < 2 * T; k += nthr) inbox[INBOX_U + k] = Unew[k];
     return;
   }
   // Savitzky-Golay: P = [hist0, hist1, U_0 .. U_{T-1}, U_{T-1}, U_{T-1}], taps [-3 12 17 12 -3]/35
   const float f0 = -3.0f / 35.0f, f1 = 12.0f / 35.0f, f2 = 17.0f / 35.0f;
-  for (int k = tid; k < 2 * T; k += 256) {
+  for (int k = tid; k < 2 * T; k += nthr) {
     const int i = k >> 1, j = k & 1;
     float pv[5];
 #pragma unroll
@@ -352,11 +372,11 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ F
       nparams = 0;
       for (int l = 0; l + 1 < p.num_layers; l++) nparams += (p.net_structure[l] + 1) * p.net_structure[l + 1];
     }
-    for (int k = tid; k < nparams; k += 256) sw[k] = p.theta_t[k];
+    for (int k = tid; k < nparams; k += nthr) sw[k] = p.theta_t[k];
   }
   __syncthreads();
   if (p.feed_back)
-    for (int k = tid; k < 2 * T; k += 256) inbox[INBOX_U + k] = Usm[k];
+    for (int k = tid; k < 2 * T; k += nthr) inbox[INBOX_U + k] = Usm[k];
   if (tid >= 32) return;
   // ---- nominal trajectory (computeNominalTraj :501-519 -> host updateState) on warp 0 ----
   const int lane = tid;
