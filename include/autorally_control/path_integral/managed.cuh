@@ -1,19 +1,18 @@
-// managed.cuh -- stream-binding base of the dynamics and cost classes (API of PI/managed.cuh:30-45).
-#ifndef MPPI_MANAGED_CUH_
-#define MPPI_MANAGED_CUH_
+// managed.cuh -- Managed: the base class the dynamics and cost types derive from; it records which CUDA stream an
+// object was bound to (API shape of PI/managed.cuh:30-45: public `stream_`, `bindToStream`).
+//
+// The reference calls cudaDeviceSynchronize() on every bind.  Here the parameters of models and costs stay on the host
+// until a controller uploads them on its own context stream, so binding is pure bookkeeping: nothing to wait for.
+#pragma once
 #include <cuda_runtime.h>
 
 namespace autorally_control {
 
-class Managed {
- public:
-  cudaStream_t stream_ = 0;  ///< stream the object is bound to (0 = the library's own stream)
+struct Managed {
+  cudaStream_t stream_ = nullptr;  // nullptr = "use the controller context's own stream"
 
-  // The reference synchronises the whole device here (PI/managed.cuh:42).  Parameters of this
-  // implementation live on the host until a controller uploads them on its own stream, so
-  // binding is pure bookkeeping and needs no device-wide synchronisation.
-  void bindToStream(cudaStream_t stream) { stream_ = stream; }
+  void bindToStream(cudaStream_t stream) noexcept { stream_ = stream; }
+  cudaStream_t boundStream() const noexcept { return stream_; }
 };
 
 }  // namespace autorally_control
-#endif
