@@ -182,23 +182,18 @@ def run_reference(args):
     if gpu_ok:
         with ref.ReferenceController(ref.REF_NN_1920, models["autorally_nnet_theta"], costmap, cp) as rc:
             rc.set_controls(U, np.zeros(4, np.float32))
-            for _ in range(max(args.warmup, 1)):
-                rc.compute_control(state, want_eps=False)
-            lat = []
-            t_all = time.perf_counter()
-            for _ in range(args.steps):
-                t0 = time.perf_counter()
-                rc.compute_control(state, want_eps=False)
-                lat.append(time.perf_counter() - t0)
-            dt = time.perf_counter() - t_all
-        lat.sort()
+            rc.time_compute_control(state, reps=max(args.warmup, 1))
+            # K consecutive computeControl(state) calls timed inside the harness (oracle/ref_harness.cu: CUDA events
+            # around the loop; the reference's own host syncs, copies and host-side smoothing / nominal rollout included)
+            ms_per_call = rc.time_compute_control(state, reps=args.steps)
+        dt = ms_per_call * 1e-3 * args.steps
         val = N_ROLLOUTS * T_STEPS * args.steps / dt
         line.update(value=val, ms_per_step=1e3 * dt / args.steps,
                     config=bench_config(1),
                     reference_impl="rdesc/autorally MPPIController<NeuralNetModel<7,2,3,6,32,32,4>,MPPICosts,1920,8,16>::computeControl, "
                                    "its own CUDA kernels and cuRAND noise, sources compiled unmodified for sm_100a (oracle/refbuild.py), "
                                    "on this B200",
-                    p50_ms=1e3 * lat[len(lat) // 2],
+                    ms_per_call_mean=ms_per_call,
                     cpu_baseline={"value": val, "unit": "rollout-steps/s", "cores": 1, "kind": "reference",
                                   "sample": "%d x reference computeControl(1920x100) from oracle/_ref (GPU kernels + 1 host thread; "
                                             "the reference has no CPU implementation of this path)" % args.steps},
