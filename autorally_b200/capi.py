@@ -37,7 +37,7 @@ EXPORTED_SYMBOLS = [
     "mppi_shard_begin_async", "mppi_shard_finish_async", "mppi_shard_result", "mppi_set_stream",
     "mppi_comm_unique_id", "mppi_comm_init", "mppi_comm_destroy", "mppi_compute_control_sharded",
     "mppi_run_resident_sharded", "mppi_compute_control_async", "mppi_compute_control_wait",
-    "mppi_bench_compute_control",
+    "mppi_bench_compute_control", "mppi_p2p_export", "mppi_p2p_init", "mppi_p2p_destroy",
 ]
 
 
@@ -80,6 +80,8 @@ def load_library():
         lib.mppi_set_gamma.argtypes = [ctypes.c_void_p, ctypes.c_float]
         lib.mppi_set_stream.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         lib.mppi_comm_init.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int]
+        lib.mppi_p2p_export.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_char_p]
+        lib.mppi_p2p_init.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int]
         _lib = lib
     return _lib
 
@@ -318,6 +320,16 @@ class MppiContext:
     def comm_init(self, unique_id: bytes, rank: int, num_ranks: int):
         assert len(unique_id) == 128
         self._ck(self.lib.mppi_comm_init(self._ctx, unique_id, int(rank), int(num_ranks)), "mppi_comm_init")
+
+    # ---- peer-memory exchange (no collective) ---------------------------------------
+    def p2p_export(self, num_ranks: int) -> bytes:
+        buf = ctypes.create_string_buffer(128)
+        self._ck(self.lib.mppi_p2p_export(self._ctx, int(num_ranks), buf), "mppi_p2p_export")
+        return buf.raw
+
+    def p2p_init(self, all_handles: bytes, rank: int, num_ranks: int):
+        assert len(all_handles) == 128 * num_ranks
+        self._ck(self.lib.mppi_p2p_init(self._ctx, all_handles, int(rank), int(num_ranks)), "mppi_p2p_init")
 
     def compute_control_sharded(self, state, U, hist=None):
         B, T = self.B, self.T

@@ -43,6 +43,16 @@ struct mppi_ctx {
   void *nccl_comm = nullptr;
   int comm_rank = 0, comm_size = 1;
   float *d_gathered = nullptr;
+  // peer-memory exchange (mppi_p2p_init): local mailbox / flags, the peers' (CUDA IPC), device tables of both
+  float *p2p_mailbox = nullptr;
+  unsigned int *p2p_flags = nullptr, *d_p2p_error = nullptr;
+  float **d_peer_mailbox = nullptr;
+  unsigned int **d_peer_flags = nullptr;
+  std::vector<void *> p2p_opened;
+  int p2p_rank = 0, p2p_size = 1;
+  unsigned int p2p_seq = 0;
+  bool p2p_send = false;  // set around the launches of a sharded step that exchanges through peer memory
+  const float *p2p_mailbox_half() const { return p2p_mailbox + (size_t)(p2p_seq & 1u) * p2p_size * B * shard_floats; }
   // model
   bool have_model = false, have_cost_params = false, have_map = false, have_inbox = false;
   int net_kind = 0;  // 0 none, 32 = 6-32-32-4, 64 = 6-64-64-64-64-4
@@ -189,6 +199,8 @@ cudaError_t launch_weighting(mppi_ctx *c) {
   p.block_partials = c->d_block_partials; p.shard = c->d_shard; p.done_counter = c->d_done;
   p.n_local = c->n_local; p.T = c->T; p.nblk = c->nblk; p.rows_per_blk = c->rows_per_blk; p.shard_floats = c->shard_floats;
   p.gamma = c->gamma;
+  p.G = c->p2p_send ? c->p2p_size : 1; p.rank = c->p2p_rank; p.B = c->B; p.seq = c->p2p_seq;
+  p.peer_mailbox = c->d_peer_mailbox; p.peer_flags = c->d_peer_flags;
   const int nrl = std::max(1, 256 / c->T);
   const size_t smem = (size_t)round_up(c->rows_per_blk, 4) * 4 + (size_t)nrl * c->T * 8;
   c->launches++;
@@ -211,6 +223,8 @@ cudaError_t launch_finalize(mppi_ctx *c, const float *gathered, int G, int last_
   p.lo0 = c->ranges[0]; p.hi0 = c->ranges[1]; p.lo1 = c->ranges[2]; p.hi1 = c->ranges[3];
   p.negate_yaw = c->negate_yaw; p.last_iter = last_iter; p.feed_back = feed_back;
   p.baseline = c->d_baseline; p.call_counter = c->d_call_counter;
+  p.p2p_flags = (c->p2p_send && gathered == c->p2p_mailbox_half()) ? c->p2p_flags : nullptr;
+  p.p2p_seq = c->p2p_seq; p.p2p_error = c->d_p2p_error;
   c->launches++;
   // after an NCCL exchange (gathered != own shard) the predecessor is not one of our kernels: plain launch
   // many batched controllers: small CTAs, so that more of the single-warp nominal trajectories are resident per SM
@@ -366,6 +380,7 @@ int mppi_destroy(mppi_ctx *c) {
   cudaSetDevice(c->device);
   if (c->stream || !c->owns_stream) cudaStreamSynchronize(c->stream);
   mppi_comm_destroy(c);
+  mppi_p2p_destroy(c);
   if (c->map_tex) cudaDestroyTextureObject(c->map_tex);
   if (c->map_array) cudaFreeArray(c->map_array);
   if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
@@ -773,6 +788,16 @@ constexpr int kNcclFloat = 7;  // ncclFloat32 (nccl.h: ncclDataType_t)
 
 // front -> all-gather of the shard records -> finalize, all on the context's stream
 int enqueue_sharded(mppi_ctx *c, int feed_back) {
+  if (c->p2p_size > 1) {
+    // peer-memory exchange fused into the weighting and finalize kernels: no collective launch at all
+    c->p2p_seq++;
+    c->p2p_send = true;
+    int rc = run_front(c, 0);
+    cudaError_t e = rc ? cudaSuccess : launch_finalize(c, c->p2p_mailbox_half(), c->p2p_size, 1, feed_back);
+    c->p2p_send = false;
+    if (rc) return rc;
+    return (int)e;
+  }
   int rc = run_front(c, 0);
   if (rc) return rc;
   const size_t count = (size_t)c->B * c->shard_floats;
@@ -823,7 +848,7 @@ int mppi_compute_control_sharded(mppi_ctx *c, const float *state, float *U, cons
   int rc = check_ready(c);
   if (rc) return rc;
   if (!state || !U) return MPPI_ERR_INVALID_ARG;
-  if (!c->nccl_comm) return MPPI_ERR_NOT_READY;
+  if (!c->nccl_comm && c->p2p_size <= 1) return MPPI_ERR_NOT_READY;
   if (c->cfg.num_iters != 1) return MPPI_ERR_UNSUPPORTED;
   CK(cudaSetDevice(c->device));
   stage_inbox(c, state, U, hist);
@@ -834,14 +859,77 @@ int mppi_compute_control_sharded(mppi_ctx *c, const float *state, float *U, cons
   if (rc) return rc;
   CK(cudaMemcpyAsync(c->h_outbox, c->d_outbox, (size_t)c->B * c->outbox_stride * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  if (c->p2p_size > 1) {
+    unsigned int err = 0;
+    CK(cudaMemcpy(&err, c->d_p2p_error, sizeof(err), cudaMemcpyDeviceToHost));
+    if (err) return MPPI_ERR_COMM;  // a peer never delivered its record (timeout in finalize_kernel)
+  }
   unpack_outbox(c, U, ss, cs, res);
+  return MPPI_OK;
+}
+
+// ---- peer-memory exchange set-up (CUDA IPC; one process per GPU on one NVSwitch box) ----
+int mppi_p2p_export(mppi_ctx *c, int num_ranks, void *handles_out /* 2 x 64 bytes: mailbox, flags */) {
+  if (!c || !handles_out || num_ranks < 2 || num_ranks > 64) return MPPI_ERR_INVALID_ARG;
+  CK(cudaSetDevice(c->device));
+  mppi_p2p_destroy(c);
+  const size_t mail = (size_t)2 * num_ranks * c->B * c->shard_floats * sizeof(float);
+  const size_t flags = (size_t)2 * num_ranks * c->B * sizeof(unsigned int);
+  CK(cudaMalloc(&c->p2p_mailbox, mail));
+  CK(cudaMalloc(&c->p2p_flags, flags));
+  CK(cudaMemset(c->p2p_mailbox, 0, mail));
+  CK(cudaMemset(c->p2p_flags, 0, flags));
+  CK(cudaMalloc(&c->d_p2p_error, sizeof(unsigned int)));
+  CK(cudaMemset(c->d_p2p_error, 0, sizeof(unsigned int)));
+  cudaIpcMemHandle_t h[2];
+  CK(cudaIpcGetMemHandle(&h[0], c->p2p_mailbox));
+  CK(cudaIpcGetMemHandle(&h[1], c->p2p_flags));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  std::memcpy(handles_out, h, sizeof(h));
+  c->p2p_size = -num_ranks;  // exported, not yet connected
+  return MPPI_OK;
+}
+
+int mppi_p2p_init(mppi_ctx *c, const void *all_handles /* [num_ranks][2][64] */, int rank, int num_ranks) {
+  if (!c || !all_handles || num_ranks < 2 || rank < 0 || rank >= num_ranks || c->p2p_size != -num_ranks) return MPPI_ERR_INVALID_ARG;
+  CK(cudaSetDevice(c->device));
+  std::vector<float *> mail(num_ranks);
+  std::vector<unsigned int *> flags(num_ranks);
+  const cudaIpcMemHandle_t *h = static_cast<const cudaIpcMemHandle_t *>(all_handles);
+  for (int g = 0; g < num_ranks; g++) {
+    if (g == rank) { mail[g] = c->p2p_mailbox; flags[g] = c->p2p_flags; continue; }
+    void *pm = nullptr, *pf = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&pm, h[2 * g], cudaIpcMemLazyEnablePeerAccess);
+    if (e == cudaSuccess) { c->p2p_opened.push_back(pm); e = cudaIpcOpenMemHandle(&pf, h[2 * g + 1], cudaIpcMemLazyEnablePeerAccess); }
+    if (e != cudaSuccess) { cudaGetLastError(); c->p2p_size = -num_ranks; return MPPI_ERR_COMM; }
+    c->p2p_opened.push_back(pf);
+    mail[g] = static_cast<float *>(pm); flags[g] = static_cast<unsigned int *>(pf);
+  }
+  CK(cudaMalloc(&c->d_peer_mailbox, num_ranks * sizeof(float *)));
+  CK(cudaMalloc(&c->d_peer_flags, num_ranks * sizeof(unsigned int *)));
+  CK(cudaMemcpy(c->d_peer_mailbox, mail.data(), num_ranks * sizeof(float *), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d_peer_flags, flags.data(), num_ranks * sizeof(unsigned int *), cudaMemcpyHostToDevice));
+  c->p2p_rank = rank; c->p2p_size = num_ranks; c->p2p_seq = 0;
+  return MPPI_OK;
+}
+
+int mppi_p2p_destroy(mppi_ctx *c) {
+  if (!c) return MPPI_ERR_INVALID_ARG;
+  if (c->stream || !c->owns_stream) cudaStreamSynchronize(c->stream);
+  for (void *p : c->p2p_opened) cudaIpcCloseMemHandle(p);
+  c->p2p_opened.clear();
+  cudaFree(c->p2p_mailbox); cudaFree(c->p2p_flags); cudaFree(c->d_p2p_error);
+  cudaFree(c->d_peer_mailbox); cudaFree(c->d_peer_flags);
+  c->p2p_mailbox = nullptr; c->p2p_flags = nullptr; c->d_p2p_error = nullptr; c->d_peer_mailbox = nullptr; c->d_peer_flags = nullptr;
+  c->p2p_size = 1; c->p2p_rank = 0; c->p2p_seq = 0;
+  cudaGetLastError();
   return MPPI_OK;
 }
 
 int mppi_run_resident_sharded(mppi_ctx *c, int steps, float *elapsed_ms) {
   int rc = check_ready(c);
   if (rc) return rc;
-  if (steps < 1 || !c->have_inbox || c->injected || !c->nccl_comm) return MPPI_ERR_INVALID_ARG;
+  if (steps < 1 || !c->have_inbox || c->injected || (!c->nccl_comm && c->p2p_size <= 1)) return MPPI_ERR_INVALID_ARG;
   CK(cudaSetDevice(c->device));
   c->launches = 0;
   CK(cudaEventRecord(c->ev0, c->stream));

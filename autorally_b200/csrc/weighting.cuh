@@ -106,7 +106,29 @@ struct WeightParams {
   unsigned int *done_counter;    // [B]
   int n_local, T, nblk, rows_per_blk, shard_floats;
   float gamma;
+  // Peer-memory exchange (multi-GPU, mppi_p2p_init): the CTA that finishes a controller's shard record also stores it
+  // into the mailbox of every GPU -- over NVLink for the peers -- and then raises that GPU's flag for (rank, controller)
+  // to `seq`.  peer_mailbox[g] = GPU g's mailbox [2][G][B][shard_floats], peer_flags[g] = its flags [2][G][B].
+  float *const *peer_mailbox;
+  unsigned int *const *peer_flags;
+  int G, rank, B;
+  unsigned int seq;  // call sequence number (> 0); parity seq & 1 selects the mailbox half
 };
+
+__device__ __forceinline__ void st_release_sys(unsigned int *p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+constexpr unsigned long long P2P_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;  // 20 s
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 
 // grid (nblk, B), block 256.  Each CTA owns rows_per_blk rollouts of one controller: it turns their
 // costs into weights in shared memory (exp-normalisation against the baseline the rollout kernel
@@ -216,6 +238,19 @@ __global__ void __launch_bounds__(256) weight_reduce_kernel(const __grid_constan
     for (; j < p.nblk; j++) a0 += __ldcg(parts + (size_t)j * p.shard_floats + k);
     shard[k] = (a0 + a1) + (a2 + a3);
   }
+  if (p.G > 1) {
+    // fused exchange: this CTA's record goes straight into every GPU's mailbox (peer stores over NVLink), then the flags
+    __syncthreads();
+    const int par = (int)(p.seq & 1u);
+    const size_t slot = (((size_t)par * p.G + p.rank) * p.B + b) * p.shard_floats;
+    for (int g = 0; g < p.G; g++) {
+      float *dst = p.peer_mailbox[g] + slot;
+      for (int k = tid; k < p.shard_floats; k += 256) dst[k] = shard[k];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < p.G) st_release_sys(p.peer_flags[tid] + ((size_t)par * p.G + p.rank) * p.B + b, p.seq);
+  }
 }
 
 // ------------------------------------------------------------------------------ finalize ----
@@ -234,6 +269,11 @@ struct FinalizeParams {
   int feed_back;          // 1: write the smoothed U back into the inbox (resident stepping)
   unsigned int *baseline; // [B] re-armed (0xffffffff) for the next rollout launch
   uint32_t *call_counter; // advanced once per launch (Philox offset of the next sampler launch)
+  // Peer-memory exchange: wait until every rank's flag for this controller reached `p2p_seq`, then read the mailbox half
+  // `p2p_seq & 1` (gathered points at it).  A rank that never arrives trips the timeout and *p2p_error is set.
+  const unsigned int *p2p_flags;  // this GPU's flags [2][G][B]; nullptr = no peer exchange
+  unsigned int p2p_seq;
+  unsigned int *p2p_error;
 };
 
 constexpr int FIN_MAX_WIDTH = 128;
@@ -315,6 +355,18 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ F
   WarpMlp32 net;
   if (p.is_nn32 && p.last_iter && tid < 32) net.load(p.theta_t, tid);
   pdl_wait();  // the shard records come from the weighting kernel (or the exchange)
+  if (p.p2p_flags != nullptr) {
+    if (tid < p.G) {
+      const unsigned int *flag = p.p2p_flags + ((size_t)(p.p2p_seq & 1u) * p.G + tid) * p.B + b;
+      // bounded wait on the wall clock: ranks may be seconds apart on their first call; a dead peer must not hang the GPU
+      const unsigned long long t0 = globaltimer_ns();
+      while (ld_acquire_sys(flag) != p.p2p_seq) {
+        __nanosleep(100);
+        if (globaltimer_ns() - t0 > P2P_TIMEOUT_NS) { atomicExch(p.p2p_error, 1u); break; }
+      }
+    }
+    __syncthreads();
+  }
 
   if (tid == 0) {
     float base = p.gathered[((size_t)0 * p.B + b) * p.shard_floats];

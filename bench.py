@@ -391,10 +391,12 @@ def main():
         dist.destroy_process_group()
 
 
-def run_sharded_large(models, costmap, cp, state, U, world, rank, local_rank, barrier, max_over_ranks, steps=5):
-    """configs[3]: 1M rollouts x 100 steps sharded over the ranks; per step ONE ncclAllGather of the (4 + 2T)-float
-    shard record per rank, issued by the library on the context's stream between the weighting
-    and finalize kernels.  Device-resident, timed with CUDA events on that stream, max over ranks."""
+def run_sharded_large(models, costmap, cp, state, U, world, rank, local_rank, barrier, max_over_ranks, steps=20):
+    """configs[3]: 1M rollouts x 100 steps sharded over the ranks; per step ONE exchange of the (4 + 2T)-float shard
+    record per rank.  Measured twice: with the peer-memory exchange fused into the weighting /
+    finalize kernels (mppi_p2p_init: NVLink stores + flags, no collective launch) and with one ncclAllGather issued by
+    the library on the context's stream between those kernels.  Device-resident, timed with CUDA events on that
+    stream, max over ranks; one untimed sharded step right before the timed ones aligns the ranks on the device."""
     import torch.distributed as dist
     from autorally_b200.capi import MppiContext
     from autorally_b200.sharding import rollout_shard
@@ -405,17 +407,31 @@ def run_sharded_large(models, costmap, cp, state, U, world, rank, local_rank, ba
     ctx = make_context("nn", models, costmap, cp, LARGE_ROLLOUTS, rollout_begin=lo, rollout_count=n, device=local_rank)
     ctx.comm_init(ids[0], rank, world)
     out = ctx.compute_control_sharded(state, U)      # initialises the device-resident state / U
-    ctx.run_resident_sharded(2)
-    barrier()
-    ms = ctx.run_resident_sharded(steps)
-    barrier()
-    ms = max_over_ranks(ms)
+
+    def timed():
+        ctx.run_resident_sharded(2)
+        barrier()
+        ctx.run_resident_sharded(1)                  # its exchange lines the ranks up on the device
+        ms = ctx.run_resident_sharded(steps)
+        barrier()
+        return max_over_ranks(ms)
+
+    ms_nccl = timed()
+    handles = [None] * world
+    dist.all_gather_object(handles, ctx.p2p_export(world))
+    ctx.p2p_init(b"".join(handles), rank, world)
+    out_p2p = ctx.compute_control_sharded(state, U)
+    ms = timed()
     sf = ctx.shard_floats()
     ctx.close()
     return {"rollouts": LARGE_ROLLOUTS, "rollouts_per_gpu": n, "steps": steps, "ms_per_step": ms / steps,
             "value": LARGE_ROLLOUTS * T_STEPS * steps / (ms * 1e-3), "unit": "rollout-steps/s", "scaling": "strong",
-            "exchange": "one ncclAllGather of %d floats per rank per step, inside the library, on the compute stream" % sf,
-            "timing": "CUDA events on the context's stream, max over ranks", "normalizer": float(out["normalizer"])}
+            "exchange": "peer-memory: the weighting kernel stores each rank's %d-float record into every GPU's mailbox over "
+                        "NVLink and raises a flag, finalize waits on the flags; no collective launch" % sf,
+            "ms_per_step_nccl_allgather": ms_nccl / steps,
+            "value_nccl_allgather": LARGE_ROLLOUTS * T_STEPS * steps / (ms_nccl * 1e-3),
+            "timing": "CUDA events on the context's stream, max over ranks", "normalizer": float(out_p2p["normalizer"]),
+            "normalizer_nccl": float(out["normalizer"])}
 
 
 if __name__ == "__main__":

@@ -188,6 +188,16 @@ int mppi_comm_init(mppi_ctx *ctx, const void *id_128_bytes, int rank, int num_ra
 int mppi_comm_destroy(mppi_ctx *ctx);
 int mppi_compute_control_sharded(mppi_ctx *ctx, const float *state, float *U, const float *control_hist,
                                  float *state_solution, float *control_solution, mppi_result *result);
+/* The same exchange WITHOUT a collective: over NVLink peer memory, fused into the kernels on either side of it.  The
+ * CTA that completes a rank's record stores it directly into every GPU's mailbox and raises a flag; finalize_kernel
+ * waits for the G flags of its controller (bounded: a missing peer yields MPPI_ERR_COMM, not a hang).  One process per
+ * GPU on one NVSwitch box.  Set-up: every rank calls mppi_p2p_export (2 x 64-byte CUDA IPC handles), the handles of all
+ * ranks are exchanged out of band in rank order, every rank calls mppi_p2p_init.  Afterwards
+ * mppi_compute_control_sharded / mppi_run_resident_sharded use this path instead of NCCL. */
+int mppi_p2p_export(mppi_ctx *ctx, int num_ranks, void *handles_out_128_bytes);
+int mppi_p2p_init(mppi_ctx *ctx, const void *all_handles /* [num_ranks][128 bytes] */, int rank, int num_ranks);
+int mppi_p2p_destroy(mppi_ctx *ctx);
+
 /* Device-resident sharded stepping (throughput measurement): `steps` sharded pipelines back to back, no host copies. */
 int mppi_run_resident_sharded(mppi_ctx *ctx, int steps, float *elapsed_ms);
 

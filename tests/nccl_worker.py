@@ -3,7 +3,7 @@
     RANK=r WORLD_SIZE=G MPPI_ID_FILE=/tmp/id python tests/nccl_worker.py
 
 Each rank owns GPU `RANK`, takes its shard of the rollouts, and runs mppi_compute_control_sharded (sampler or injected
-noise -> rollouts -> local record -> ONE ncclAllGather -> finalize).  Every rank also computes the unsharded answer on
+noise -> rollouts -> local record -> ONE ncclAllGather -> finalize), then the same with the peer-memory exchange.  Every rank also computes the unsharded answer on
 its own GPU and asserts the sharded result equals it (<= 1e-5 relative): results must not depend on the number of GPUs.
 The NCCL unique id travels through a file, so no torch.distributed is involved.
 """
@@ -69,7 +69,39 @@ def main():
         # (3) device-resident sharded stepping runs and is timed on the device
         ms = ctx.run_resident_sharded(5)
         assert ms > 0
-        print("rank %d/%d ok: shard [%d, %d), sharded step %.3f ms" % (rank, world, lo, lo + n, ms / 5))
+        # (4) the same exchange without a collective: peer-memory stores fused into the weighting kernel, flag wait in
+        # finalize (mppi_p2p_export / mppi_p2p_init; CUDA IPC handles travel through files, in rank order)
+        mine = ctx.p2p_export(world)
+        with open("%s.p2p.%d.tmp" % (id_file, rank), "wb") as f:
+            f.write(mine)
+        os.replace("%s.p2p.%d.tmp" % (id_file, rank), "%s.p2p.%d" % (id_file, rank))
+        handles = b""
+        for r in range(world):
+            t0 = time.time()
+            while not os.path.exists("%s.p2p.%d" % (id_file, r)):
+                if time.time() - t0 > 120:
+                    raise TimeoutError("no peer-memory handle from rank %d" % r)
+                time.sleep(0.05)
+            handles += open("%s.p2p.%d" % (id_file, r), "rb").read()
+        ctx.p2p_init(handles, rank, world)
+        full.set_noise(eps); ctx.set_noise(eps[lo:lo + n])
+        for rep in range(3):   # both mailbox halves and the sequence numbers
+            want = full.compute_control(state, U, hist)
+            got = ctx.compute_control_sharded(state, U, hist)
+            assert got["baseline"] == want["baseline"], ("p2p", got["baseline"], want["baseline"])
+            for k in ("U", "state_solution", "control_solution", "normalizer", "trajectory_cost"):
+                assert rel(got[k], want[k]) < 1e-5, ("p2p", rep, k, rel(got[k], want[k]))
+        full.use_sampler(); ctx.use_sampler()
+        full.seed(78, 5); ctx.seed(78, 5)
+        want = full.compute_control(state, U, hist)
+        got = ctx.compute_control_sharded(state, U, hist)
+        for k in ("U", "state_solution", "normalizer"):
+            assert rel(got[k], want[k]) < 1e-5, ("p2p sampler", k, rel(got[k], want[k]))
+        ctx.run_resident_sharded(5)
+        ms_p2p = ctx.run_resident_sharded(20)
+        assert ms_p2p > 0
+        print("rank %d/%d ok: shard [%d, %d), sharded step %.3f ms (NCCL all-gather), %.3f ms (peer-memory exchange)"
+              % (rank, world, lo, lo + n, ms / 5, ms_p2p / 20))
 
 
 if __name__ == "__main__":
