@@ -1,0 +1,385 @@
+// rollout_tc.cu -- the filled-GPU rollout kernel with the MLP contraction on the 5th-generation tensor cores.
+//
+// Replaces rolloutKernel (PI/mppi_controller.cu:72-184) + NeuralNetModel<7,2,3,6,32,32,4>::computeDynamics
+// (PI/neural_net_model.cu:357-410) for large rollout counts.  One thread owns one rollout (bookkeeping, clamp, costs,
+// kinematics, Euler step: exactly the code of rollout.cuh); the three layer contractions of a 128-rollout tile are
+// tcgen05.mma instructions (M = 128 rollouts, N = 32 / 32 / 16 neurons):
+//
+//   * A (the activations) lives in TENSOR MEMORY: thread r owns TMEM lane r, writes its own row with tcgen05.st and the
+//     MMA reads it from there -- no shared-memory round trip, no swizzled layouts, no cross-thread traffic at all.
+//   * B (the weights) is staged once per CTA in shared memory in the canonical K-major no-swizzle layout.
+//   * D (the pre-activations) accumulates in TMEM in FP32 and comes back with tcgen05.ld, one row per thread.
+//
+// FP32 accuracy on FP16 tensor cores: a single FP16 / TF32 pass (11-bit significands) misses the 1e-4 parity bar by an
+// order of magnitude after 100 recurrent steps, so every operand is split into two FP16 halves,
+// x = x_hi + x_lo (|x_lo| <= 2^-11 |x|; the split is exact in FP32), and each layer is three accumulating passes
+//   D = A_hi B_hi + A_lo B_hi + A_hi B_lo          (dropped term A_lo B_lo ~ 2^-22 relative),
+// issued as K = 16 chunks.  FP16 products are exact in the FP32 accumulator.  The bias rides along as one more K chunk
+// (a constant A chunk [1, 1, 0, ...] against [b_hi, b_lo, 0, ...]); layer 1 (6 inputs) carries it in its K padding.
+// The hidden layers' weights and biases are pre-multiplied by 2 log2(e), so tanh(x) = 1 - 2 / (2^x' + 1) needs no
+// multiply in the epilogue: MUFU.EX2, FADD, MUFU.RCP, FFMA, then the hi/lo split for the next layer.
+//
+// Tensor work per tile and timestep: 2 + 7 + 7 MMAs = 16 + 112 + 56 = 184 tensor-pipe cycles for 128 rollout-steps
+// (1.4 cycles per rollout-step, B300_MICROARCH.md: M=128 costs N/2 cycles per K chunk); the FFMA2 kernel spends 10.5
+// FMA-pipe cycles per rollout-step on the same contraction.  What remains on the CUDA cores is the tanh epilogue
+// (2 MUFU per neuron: 8.6 cycles per rollout-step at 16 MUFU/clk/SM), the costs and the kinematics.
+//
+// Synchronisation per layer: tcgen05.st -> wait::st -> fence::before_thread_sync -> bar.sync -> one elected thread issues
+// the MMAs and a tcgen05.commit onto an mbarrier -> everybody waits on the mbarrier -> fence::after_thread_sync ->
+// tcgen05.ld.  Four CTAs (tiles) per SM, 128 TMEM columns each, hide that round trip behind each other's epilogues.
+#include <cuda_fp16.h>
+#include "rollout.cuh"
+#include "rollout_launch.h"
+
+namespace mppi {
+namespace tc {
+
+constexpr int TILE = 128;         // rollouts per CTA = TMEM lanes
+constexpr int TMEM_COLS = 128;    // allocation (power of two); 4 CTAs per SM
+constexpr int COL_D = 0;          // accumulator, 32 columns
+constexpr int COL_A = 32;         // activations: [hi(0..15) | lo(0..15) | hi(16..31) | lo(16..31)], 8 columns each
+constexpr int COL_ONES = 64;      // constant bias chunk [1, 1, 0, ..., 0]
+constexpr float TANH_SCALE = 2.88539008177792681472f;  // 2 log2(e)
+
+// shared-memory B matrices (FP16, canonical K-major no-swizzle: 8 rows x 16 bytes core matrices)
+constexpr int OFF_B1A = 0;               // N=32 K=16: [W1_hi | b1_hi] twice (against [a_hi | a_lo])
+constexpr int OFF_B1B = OFF_B1A + 1024;  // N=32 K=16: [W1_lo | b1_lo], 0
+constexpr int OFF_B2H = OFF_B1B + 1024;  // N=32 K=32
+constexpr int OFF_B2L = OFF_B2H + 2048;
+constexpr int OFF_B2B = OFF_B2L + 2048;  // N=32 K=16 bias chunk
+constexpr int OFF_B3H = OFF_B2B + 1024;  // N=16 K=32 (4 real output rows)
+constexpr int OFF_B3L = OFF_B3H + 1024;
+constexpr int OFF_B3B = OFF_B3L + 1024;  // N=16 K=16
+constexpr int B_BYTES = OFF_B3B + 512;
+// keeps residency at 4 CTAs per SM (4 x 128 TMEM columns): a fifth CTA would only spin in tcgen05.alloc
+constexpr int SMEM_PAD_BYTES = 46 * 1024;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// element (n, k) of an N x K FP16 matrix: core matrices ordered [k / 8][n / 8]
+__device__ __forceinline__ int b_off(int N, int n, int k) { return ((k >> 3) * (N >> 3) + (n >> 3)) * 128 + (n & 7) * 16 + (k & 7) * 2; }
+
+// SM100 shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp): start >> 4 [0,14), LBO >> 4 [16,30) = byte
+// distance between the two 16-byte K halves, SBO >> 4 [32,46) = byte distance between 8-row groups, version 1 [46,48),
+// layout type 0 = no swizzle [61,64).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, int N) {
+  const uint32_t lbo = (uint32_t)(N >> 3) * 128u, sbo = 128u;
+  const uint32_t lo = ((saddr & 0x3FFFFu) >> 4) | ((lbo >> 4) << 16);
+  const uint32_t hi = (sbo >> 4) | (1u << 14);
+  return ((uint64_t)hi << 32) | lo;
+}
+// one K = 16 chunk = two core-matrix columns
+__device__ __forceinline__ uint64_t chunk_desc(uint32_t saddr, int N, int chunk) { return make_desc(saddr + (uint32_t)chunk * 2u * (uint32_t)(N >> 3) * 128u, N); }
+
+// instruction descriptor: D = F32 [4,6), A = B = F16 (0), both K-major, N >> 3 [17,23), M >> 4 [24,29)
+__host__ __device__ constexpr uint32_t idesc(int M, int N) { return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
+
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t id, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(id), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// bounded: a mis-programmed MMA must end as wrong numbers (caught by the parity tests), never as a hung GPU
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+#pragma unroll 1
+  for (int spin = 0; spin < (1 << 22); spin++) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return true;
+  }
+  return false;
+}
+
+__device__ __forceinline__ void tmem_st8(uint32_t addr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(addr), "r"(v[0]), "r"(v[1]),
+               "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t addr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(addr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t addr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(addr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t addr, float (&v)[4]) {
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
+#pragma unroll
+  for (int i = 0; i < 4; i++) v[i] = __uint_as_float(r[i]);
+}
+
+// x0, x1 -> packed FP16 pair of the high parts (x0 in the low half = the smaller k) and of the residuals
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t &hi, uint32_t &lo) {
+  const __half2 h = __floats2half2_rn(x0, x1);
+  const float2 f = __half22float2(h);
+  const __half2 l = __floats2half2_rn(__fsub_rn(x0, f.x), __fsub_rn(x1, f.y));
+  hi = *reinterpret_cast<const uint32_t *>(&h);
+  lo = *reinterpret_cast<const uint32_t *>(&l);
+}
+
+// tanh of pre-activations already scaled by 2 log2(e)
+__device__ __forceinline__ float tanh_prescaled(float x) {
+  const float r = rcp_approx(__fadd_rn(ex2_approx(x), 1.0f));
+  return fmaf(-2.0f, r, 1.0f);
+}
+
+// 16 pre-activations -> 8 columns of hi pairs, 8 columns of lo pairs
+__device__ __forceinline__ void activate16(const float (&v)[16], uint32_t (&out)[16]) {
+#pragma unroll
+  for (int j = 0; j < 8; j++) split2(tanh_prescaled(v[2 * j]), tanh_prescaled(v[2 * j + 1]), out[j], out[8 + j]);
+}
+
+__device__ __forceinline__ void put_split(unsigned char *hi_base, unsigned char *lo_base, int N, int n, int k, float x) {
+  const __half h = __float2half_rn(x);
+  const __half l = __float2half_rn(__fsub_rn(x, __half2float(h)));
+  *reinterpret_cast<__half *>(hi_base + b_off(N, n, k)) = h;
+  if (lo_base) *reinterpret_cast<__half *>(lo_base + b_off(N, n, k)) = l;
+}
+
+__global__ void __launch_bounds__(TILE, 4) rollout_tc_kernel(const __grid_constant__ RolloutParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) unsigned long long mma_bar;
+  __shared__ uint32_t tmem_base_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+
+  // ---- prologue: weights -> FP16 hi / lo B matrices in shared memory (theta_t: per layer Wt[k][j], then b[j]) ----
+  for (int i = tid; i < B_BYTES / 16; i += TILE) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+  {
+    const float *th = p.theta_t;
+    for (int i = tid; i < 6 * 32; i += TILE) {  // layer 1 weights, scaled
+      const int k = i >> 5, n = i & 31;
+      const float w = __fmul_rn(th[i], TANH_SCALE);
+      put_split(smem + OFF_B1A, smem + OFF_B1B, 32, n, k, w);
+      put_split(smem + OFF_B1A, nullptr, 32, n, 8 + k, w);
+    }
+    if (tid < 32) {
+      const float b = __fmul_rn(th[192 + tid], TANH_SCALE);  // b1 -> K slot 6 (the input carries 1.0 there)
+      put_split(smem + OFF_B1A, smem + OFF_B1B, 32, tid, 6, b);
+      put_split(smem + OFF_B1A, nullptr, 32, tid, 8 + 6, b);
+      const float b2 = __fmul_rn(th[224 + 1024 + tid], TANH_SCALE);  // b2 -> bias chunk: k = 0 hi, k = 1 lo
+      const __half h = __float2half_rn(b2);
+      *reinterpret_cast<__half *>(smem + OFF_B2B + b_off(32, tid, 0)) = h;
+      *reinterpret_cast<__half *>(smem + OFF_B2B + b_off(32, tid, 1)) = __float2half_rn(__fsub_rn(b2, __half2float(h)));
+    }
+    for (int i = tid; i < 32 * 32; i += TILE) {  // layer 2
+      const int k = i >> 5, n = i & 31;
+      put_split(smem + OFF_B2H, smem + OFF_B2L, 32, n, k, __fmul_rn(th[224 + i], TANH_SCALE));
+    }
+    for (int i = tid; i < 32 * 4; i += TILE) {  // layer 3 (linear output, no scale)
+      const int k = i >> 2, n = i & 3;
+      put_split(smem + OFF_B3H, smem + OFF_B3L, 16, n, k, th[1280 + i]);
+    }
+    if (tid < 4) {
+      const float b3 = th[1408 + tid];
+      const __half h = __float2half_rn(b3);
+      *reinterpret_cast<__half *>(smem + OFF_B3B + b_off(16, tid, 0)) = h;
+      *reinterpret_cast<__half *>(smem + OFF_B3B + b_off(16, tid, 1)) = __float2half_rn(__fsub_rn(b3, __half2float(h)));
+    }
+  }
+  const uint32_t bar = smem_u32(&mma_bar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy weight stores -> visible to the tensor core
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem = tmem_base_slot;
+  const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);  // this warp's 32 TMEM lanes
+
+  const uint32_t sb = smem_u32(smem);
+  constexpr uint32_t ID32 = idesc(128, 32), ID16 = idesc(128, 16);
+
+  {  // constant bias chunk: k = 0, 1 are 1.0 (hi and lo of the bias), the rest 0
+    uint32_t ones[8] = {0x3C003C00u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    tmem_st8(lane_base + COL_ONES, ones);
+  }
+
+  // ---- rollout bookkeeping (rollout.cuh, R = 1) ----
+  const long long total = (long long)p.B * p.n_local;
+  const long long g0 = (long long)blockIdx.x * TILE + tid;
+  const bool valid = g0 < total;
+  const long long gc = valid ? g0 : 0;  // idle threads shadow rollout 0 (they must take part in every barrier) and store nothing
+  const int ctrl = (int)(gc / p.n_local);
+  const int lr0 = (int)(gc - (long long)ctrl * p.n_local);
+  const float *inbox = p.inbox + (size_t)ctrl * p.inbox_stride;
+  const float2 *U = reinterpret_cast<const float2 *>(inbox + INBOX_U);
+  float s[S_DIM];
+#pragma unroll
+  for (int k = 0; k < S_DIM; k++) s[k] = inbox[INBOX_STATE + k];
+  float running = 0.0f;
+  int crash = 0;
+  const int rg = p.r_begin + lr0;
+  const bool noise_free = (rg == 0), pure_noise = (rg >= p.pure_noise_from);
+  float2 *row = reinterpret_cast<float2 *>(p.du) + (size_t)gc * p.T;
+  uint32_t phase = 0;
+  bool ok = true;
+
+  for (int i = 0; i < p.T; i++) {
+    const float2 Ui = U[i];
+    // PI/mppi_controller.cu:130-155
+    const float2 e = row[i];
+    float du0, du1, u0, u1;
+    if (noise_free || i < p.opt_delay) {
+      du0 = 0.0f; du1 = 0.0f; u0 = Ui.x; u1 = Ui.y;
+    } else if (pure_noise) {
+      du0 = __fmul_rn(e.x, p.nu0); du1 = __fmul_rn(e.y, p.nu1); u0 = du0; u1 = du1;
+    } else {
+      du0 = __fmul_rn(e.x, p.nu0); du1 = __fmul_rn(e.y, p.nu1);
+      u0 = __fadd_rn(Ui.x, du0); u1 = __fadd_rn(Ui.y, du1);
+    }
+    if (valid) row[i] = make_float2(u0, u1);  // un-clamped write-back (:153)
+    u0 = u0 < p.lo0 ? p.lo0 : (u0 > p.hi0 ? p.hi0 : u0);  // enforceConstraints
+    u1 = u1 < p.lo1 ? p.lo1 : (u1 > p.hi1 ? p.hi1 : u1);
+
+    // ---- layer 1: a = [roll, u_x, u_y, yaw rate, steering, throttle, 1 (bias), 0] as [a_hi | a_lo], one K = 16 chunk ----
+    {
+      uint32_t a[8];
+      split2(s[3], s[4], a[0], a[4]);
+      split2(s[5], s[6], a[1], a[5]);
+      split2(u0, u1, a[2], a[6]);
+      a[3] = 0x00003C00u;  // (1.0, 0)
+      a[7] = 0u;
+      tmem_st8(lane_base + COL_A, a);
+    }
+    wait_st();
+    fence_before();
+    __syncthreads();
+    if (warp == 0) {
+      if (tid == 0) {
+        fence_after();
+        mma_ts(tmem + COL_D, tmem + COL_A, chunk_desc(sb + OFF_B1A, 32, 0), ID32, 0u);
+        mma_ts(tmem + COL_D, tmem + COL_A, chunk_desc(sb + OFF_B1B, 32, 0), ID32, 1u);
+        mma_commit(bar);
+      }
+      __syncwarp();
+    }
+    // the running cost of this step overlaps the MMA round trip (state before the dynamics, PI/mppi_controller.cu:162-165)
+    if (i > 0) {
+      const float c = running_cost_step(p.cp, p.tex, s, u0, u1, du0, du1, p.nu0, p.nu1, crash);
+      running = (float)((double)running + (double)__fsub_rn(c, running) * p.inv_step[i]);
+    }
+    ok = mbar_wait(bar, phase) && ok;
+    phase ^= 1u;
+    fence_after();
+
+    // ---- layers 2 and 3: tanh epilogue -> hi / lo activations back into TMEM -> 7 MMAs each ----
+#pragma unroll
+    for (int layer = 0; layer < 2; layer++) {
+      {
+        float v[16];
+        uint32_t h[16];
+        tmem_ld16(lane_base + COL_D, v);
+        wait_ld();
+        activate16(v, h);
+        tmem_st16(lane_base + COL_A, h);
+        tmem_ld16(lane_base + COL_D + 16, v);
+        wait_ld();
+        activate16(v, h);
+        tmem_st16(lane_base + COL_A + 16, h);
+      }
+      wait_st();
+      fence_before();
+      __syncthreads();
+      if (warp == 0) {
+        if (tid == 0) {
+          fence_after();
+          const int N = layer == 0 ? 32 : 16;
+          const uint32_t id = layer == 0 ? ID32 : ID16;
+          const uint32_t bh = sb + (layer == 0 ? OFF_B2H : OFF_B3H), bl = sb + (layer == 0 ? OFF_B2L : OFF_B3L);
+          const uint32_t bb = sb + (layer == 0 ? OFF_B2B : OFF_B3B);
+          mma_ts(tmem + COL_D, tmem + COL_ONES, chunk_desc(bb, N, 0), id, 0u);        // bias
+          mma_ts(tmem + COL_D, tmem + COL_A + 8, chunk_desc(bh, N, 0), id, 1u);       // lo(0..15)  x W_hi
+          mma_ts(tmem + COL_D, tmem + COL_A + 24, chunk_desc(bh, N, 1), id, 1u);      // lo(16..31) x W_hi
+          mma_ts(tmem + COL_D, tmem + COL_A + 0, chunk_desc(bl, N, 0), id, 1u);       // hi(0..15)  x W_lo
+          mma_ts(tmem + COL_D, tmem + COL_A + 16, chunk_desc(bl, N, 1), id, 1u);      // hi(16..31) x W_lo
+          mma_ts(tmem + COL_D, tmem + COL_A + 0, chunk_desc(bh, N, 0), id, 1u);       // hi x W_hi
+          mma_ts(tmem + COL_D, tmem + COL_A + 16, chunk_desc(bh, N, 1), id, 1u);
+          mma_commit(bar);
+        }
+        __syncwarp();
+      }
+      if (layer == 1) break;
+      ok = mbar_wait(bar, phase) && ok;
+      phase ^= 1u;
+      fence_after();
+    }
+    // kinematics (PI/neural_net_model.cu:346-355, precise sinf / cosf) while the last layer is in flight
+    float sn, cs;
+    sincosf(s[2], &sn, &cs);
+    const float d0 = fmaf(cs, s[4], -__fmul_rn(sn, s[5]));
+    const float d1 = fmaf(sn, s[4], __fmul_rn(cs, s[5]));
+    const float d2 = p.negate_yaw ? -s[6] : s[6];
+    ok = mbar_wait(bar, phase) && ok;
+    phase ^= 1u;
+    fence_after();
+    float o[4];
+    tmem_ld4(lane_base + COL_D, o);
+    wait_ld();
+    // incrementState, PI/neural_net_model.cu:334-344
+    s[0] = fmaf(d0, p.dt, s[0]);
+    s[1] = fmaf(d1, p.dt, s[1]);
+    s[2] = fmaf(d2, p.dt, s[2]);
+#pragma unroll
+    for (int k = 0; k < 4; k++) s[3 + k] = fmaf(o[k], p.dt, s[3 + k]);
+    if (fabsf(s[3]) >= 1.57f) crash = 1;  // getCrash, PI/costs.cu:301-305
+  }
+
+  // ---- epilogue: costs, crash flags, min-cost baseline; release the tensor memory ----
+  if (!ok) running = __int_as_float(0x7fc00000);  // the MMA never signalled: poison the result (tests catch it)
+  unsigned int best = 0xffffffffu;
+  if (valid) {
+    p.costs[g0] = running;
+    p.crash[g0] = (unsigned char)crash;
+    best = float_to_ordered(running);
+  }
+  const unsigned int wbest = __reduce_min_sync(0xffffffffu, best);
+  const int wctrl = __shfl_sync(0xffffffffu, ctrl, 0);
+  if ((tid & 31) == 0 && wbest != 0xffffffffu) atomicMin(p.baseline + wctrl, wbest);
+  fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+}
+
+}  // namespace tc
+
+cudaError_t launch_rollout_nn32_tc(const RolloutParams &p, cudaStream_t st) {
+  const long long total = (long long)p.B * p.n_local;
+  const unsigned grid = (unsigned)((total + tc::TILE - 1) / tc::TILE);
+  tc::rollout_tc_kernel<<<grid, tc::TILE, tc::SMEM_PAD_BYTES, st>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace mppi

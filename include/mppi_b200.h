@@ -53,7 +53,8 @@ enum {
   MPPI_ROLLOUT_LANES8 = 5,  /* one rollout across 8 / 16 / 32 lanes, cost evaluation deferred and */
   MPPI_ROLLOUT_LANES16 = 6, /* spread over the lanes: the latency configurations (1920 rollouts -> 32) */
   MPPI_ROLLOUT_LANES32 = 7,
-  MPPI_ROLLOUT_HALF16 = 9   /* one rollout per half-warp, FFMA2 over neuron pairs, deferred running mean: the latency default */
+  MPPI_ROLLOUT_HALF16 = 9,  /* one rollout per half-warp, FFMA2 over neuron pairs, deferred running mean: the latency default */
+  MPPI_ROLLOUT_TENSOR = 10  /* one rollout per thread, layer contractions on tcgen05 (FP16 hi/lo split, A in tensor memory) */
 };
 
 /* Replaces the MPPIController template/ctor arguments (PI/mppi_controller.cuh:52-53,101-102) plus the

@@ -76,7 +76,7 @@ def check_pair(want, got, cost_tol=1e-4, u_tol=1e-4):
     assert got["launches"] >= 3
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 5, 6, 7, 9])
+@pytest.mark.parametrize("variant", [1, 2, 3, 5, 6, 7, 9, 10])
 @pytest.mark.parametrize("speed", [0.0, 4.0, 8.0])
 def test_nn_1920x100_matches_oracle(models, costmap, variant, speed):
     """BASELINE config 2: path_integral_nn, 1920 rollouts x 100 steps, synthetic ellipse costmap."""
@@ -84,7 +84,7 @@ def test_nn_1920x100_matches_oracle(models, costmap, variant, speed):
     check_pair(want, got)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 5, 7, 9])
+@pytest.mark.parametrize("variant", [1, 2, 5, 7, 9, 10])
 @pytest.mark.parametrize("gamma", [0.15, 0.01])
 def test_nn_spread_weights_match_oracle(models, costmap, variant, gamma):
     """Flat top of the ellipse at 4 m/s: ~30% of the rollouts survive and the weights are spread over many
