@@ -176,7 +176,7 @@ cudaError_t launch_rollout(mppi_ctx *c) {
     case MPPI_ROLLOUT_LANES8: return launch_rollout_nn32_lanes(p, c->stream, 8);
     case MPPI_ROLLOUT_LANES16: return launch_rollout_nn32_lanes(p, c->stream, 16);
     case MPPI_ROLLOUT_LANES32: return launch_rollout_nn32_lanes(p, c->stream, 32);
-    case MPPI_ROLLOUT_TENSOR: return launch_rollout_nn32_tc(p, c->stream);
+    case MPPI_ROLLOUT_TENSOR: return launch_rollout_nn32_tc(p, c->stream, c->theta_t.data());
     case MPPI_ROLLOUT_HALF16: return launch_rollout_nn32_half(p, c->stream, c->pdl && !c->injected);
     default: return launch_rollout_nn32_r1(p, c->stream, small);
   }

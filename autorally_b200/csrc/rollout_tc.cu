@@ -14,20 +14,25 @@
 // order of magnitude after 100 recurrent steps, so every operand is split into two FP16 halves,
 // x = x_hi + x_lo (|x_lo| <= 2^-11 |x|; the split is exact in FP32), and each layer is three accumulating passes
 //   D = A_hi B_hi + A_lo B_hi + A_hi B_lo          (dropped term A_lo B_lo ~ 2^-22 relative),
-// issued as K = 16 chunks.  FP16 products are exact in the FP32 accumulator.  The bias rides along as one more K chunk
-// (a constant A chunk [1, 1, 0, ...] against [b_hi, b_lo, 0, ...]); layer 1 (6 inputs) carries it in its K padding.
-// The hidden layers' weights and biases are pre-multiplied by 2 log2(e), so tanh(x) = 1 - 2 / (2^x' + 1) needs no
-// multiply in the epilogue: MUFU.EX2, FADD, MUFU.RCP, FFMA, then the hi/lo split for the next layer.
+// issued as K = 16 chunks.  FP16 products are exact in the FP32 accumulator.
 //
-// Tensor work per tile and timestep: 2 + 7 + 7 MMAs = 16 + 112 + 56 = 184 tensor-pipe cycles for 128 rollout-steps
-// (1.4 cycles per rollout-step, B300_MICROARCH.md: M=128 costs N/2 cycles per K chunk); the FFMA2 kernel spends 10.5
-// FMA-pipe cycles per rollout-step on the same contraction.  What remains on the CUDA cores is the tanh epilogue
-// (2 MUFU per neuron: 8.6 cycles per rollout-step at 16 MUFU/clk/SM), the costs and the kinematics.
+// The tanh epilogue is what remains on the CUDA cores, and the MUFU unit (16 results/clk/SM) is its bottleneck, so it
+// is written to need as few MUFU results as possible.  The hidden layers' weights are pre-multiplied by 2 log2(e), and
+// the bias is folded into the exponential: 2^(x' + b') = 2^x' * 2^b' with 2^b' a kernel constant, so
+//   tanh(x + b) = 1 - 2 / (2^x' 2^b' + 1):   MUFU.EX2, one FFMA for "* 2^b' + 1", a reciprocal, one FFMA;
+// and the reciprocals of FOUR neurons share ONE MUFU.RCP (1/(d0 d1 d2 d3) and five packed multiplies; every d is
+// clamped to 2^30, where tanh is 1 to the last bit, so the product cannot overflow): 5 MUFU per 4 neurons, not 8.
+//
+// Tensor work per tile and timestep: 2 + 6 + 6 MMAs = 16 + 96 + 48 = 160 tensor-pipe cycles for 128 rollout-steps
+// (1.25 cycles per rollout-step, B300_MICROARCH.md: M=128 costs N/2 cycles per K chunk); the FFMA2 kernel spends 10.5
+// FMA-pipe cycles per rollout-step on the same contraction.
 //
 // Synchronisation per layer: tcgen05.st -> wait::st -> fence::before_thread_sync -> bar.sync -> one elected thread issues
 // the MMAs and a tcgen05.commit onto an mbarrier -> everybody waits on the mbarrier -> fence::after_thread_sync ->
-// tcgen05.ld.  Four CTAs (tiles) per SM, 128 TMEM columns each, hide that round trip behind each other's epilogues.
+// tcgen05.ld.  Eight CTAs (tiles) per SM, 64 TMEM columns and 64 registers each, hide that round trip behind each other's
+// epilogues.
 #include <cuda_fp16.h>
+#include <cmath>
 #include "rollout.cuh"
 #include "rollout_launch.h"
 
@@ -35,24 +40,21 @@ namespace mppi {
 namespace tc {
 
 constexpr int TILE = 128;         // rollouts per CTA = TMEM lanes
-constexpr int TMEM_COLS = 128;    // allocation (power of two); 4 CTAs per SM
+constexpr int TMEM_COLS = 64;     // allocation (power of two); 8 CTAs per SM
 constexpr int COL_D = 0;          // accumulator, 32 columns
 constexpr int COL_A = 32;         // activations: [hi(0..15) | lo(0..15) | hi(16..31) | lo(16..31)], 8 columns each
-constexpr int COL_ONES = 64;      // constant bias chunk [1, 1, 0, ..., 0]
 constexpr float TANH_SCALE = 2.88539008177792681472f;  // 2 log2(e)
 
 // shared-memory B matrices (FP16, canonical K-major no-swizzle: 8 rows x 16 bytes core matrices)
-constexpr int OFF_B1A = 0;               // N=32 K=16: [W1_hi | b1_hi] twice (against [a_hi | a_lo])
-constexpr int OFF_B1B = OFF_B1A + 1024;  // N=32 K=16: [W1_lo | b1_lo], 0
+constexpr int OFF_B1A = 0;               // N=32 K=16: W1_hi twice (against [a_hi | a_lo])
+constexpr int OFF_B1B = OFF_B1A + 1024;  // N=32 K=16: W1_lo, 0
 constexpr int OFF_B2H = OFF_B1B + 1024;  // N=32 K=32
 constexpr int OFF_B2L = OFF_B2H + 2048;
-constexpr int OFF_B2B = OFF_B2L + 2048;  // N=32 K=16 bias chunk
-constexpr int OFF_B3H = OFF_B2B + 1024;  // N=16 K=32 (4 real output rows)
+constexpr int OFF_B3H = OFF_B2L + 2048;  // N=16 K=32 (4 real output rows)
 constexpr int OFF_B3L = OFF_B3H + 1024;
-constexpr int OFF_B3B = OFF_B3L + 1024;  // N=16 K=16
-constexpr int B_BYTES = OFF_B3B + 512;
-// keeps residency at 4 CTAs per SM (4 x 128 TMEM columns): a fifth CTA would only spin in tcgen05.alloc
-constexpr int SMEM_PAD_BYTES = 46 * 1024;
+constexpr int B_BYTES = OFF_B3L + 1024;
+// keeps residency at 8 CTAs per SM (8 x 64 TMEM columns): a ninth CTA would only spin in tcgen05.alloc
+constexpr int SMEM_PAD_BYTES = 24 * 1024;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -143,16 +145,47 @@ __device__ __forceinline__ void split2(float x0, float x1, uint32_t &hi, uint32_
   lo = *reinterpret_cast<const uint32_t *>(&l);
 }
 
-// tanh of pre-activations already scaled by 2 log2(e)
-__device__ __forceinline__ float tanh_prescaled(float x) {
-  const float r = rcp_approx(__fadd_rn(ex2_approx(x), 1.0f));
-  return fmaf(-2.0f, r, 1.0f);
+// Epilogue constants, in the kernel parameter block (constant bank): 2^(2 log2(e) b) per hidden neuron, b3 as is.
+struct TcEpilogue {
+  float eb1[32], eb2[32], b3[4];
+};
+
+// tanh(x + b) for four neurons; x already scaled by 2 log2(e), eb = 2^(scaled bias).  One MUFU.RCP for all four.
+__device__ __forceinline__ void tanh4(float x0, float x1, float x2, float x3, float2 eb01, float2 eb23, float2 &y01, float2 &y23) {
+  const float2 one = make_float2(1.0f, 1.0f);
+  float2 d01 = __ffma2_rn(make_float2(ex2_approx(x0), ex2_approx(x1)), eb01, one);
+  float2 d23 = __ffma2_rn(make_float2(ex2_approx(x2), ex2_approx(x3)), eb23, one);
+  const float cap = 1073741824.0f;  // 2^30: 1 - 2/d is 1 to the last bit beyond it; keeps d0 d1 d2 d3 finite
+  d01.x = fminf(d01.x, cap); d01.y = fminf(d01.y, cap);
+  d23.x = fminf(d23.x, cap); d23.y = fminf(d23.y, cap);
+  const float2 q = __fmul2_rn(d01, d23);                   // (d0 d2, d1 d3)
+  const float r = rcp_approx(__fmul_rn(q.x, q.y));         // 1 / (d0 d1 d2 d3)
+  const float2 iq = __fmul2_rn(make_float2(r, r), make_float2(q.y, q.x));  // (1 / (d0 d2), 1 / (d1 d3))
+  const float2 i01 = __fmul2_rn(iq, d23);                  // (1 / d0, 1 / d1)
+  const float2 i23 = __fmul2_rn(iq, d01);                  // (1 / d2, 1 / d3)
+  const float2 m2 = make_float2(-2.0f, -2.0f);
+  y01 = __ffma2_rn(m2, i01, one);
+  y23 = __ffma2_rn(m2, i23, one);
+}
+
+__device__ __forceinline__ void split2v(float2 y, uint32_t &hi, uint32_t &lo) {
+  const __half2 h = __floats2half2_rn(y.x, y.y);
+  const float2 f = __half22float2(h);
+  const float2 d = __fadd2_rn(y, make_float2(-f.x, -f.y));
+  const __half2 l = __floats2half2_rn(d.x, d.y);
+  hi = *reinterpret_cast<const uint32_t *>(&h);
+  lo = *reinterpret_cast<const uint32_t *>(&l);
 }
 
 // 16 pre-activations -> 8 columns of hi pairs, 8 columns of lo pairs
-__device__ __forceinline__ void activate16(const float (&v)[16], uint32_t (&out)[16]) {
+__device__ __forceinline__ void activate16(const float (&v)[16], const float *eb, uint32_t (&out)[16]) {
 #pragma unroll
-  for (int j = 0; j < 8; j++) split2(tanh_prescaled(v[2 * j]), tanh_prescaled(v[2 * j + 1]), out[j], out[8 + j]);
+  for (int j = 0; j < 4; j++) {
+    float2 y01, y23;
+    tanh4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3], make_float2(eb[4 * j], eb[4 * j + 1]), make_float2(eb[4 * j + 2], eb[4 * j + 3]), y01, y23);
+    split2v(y01, out[2 * j], out[8 + 2 * j]);
+    split2v(y23, out[2 * j + 1], out[8 + 2 * j + 1]);
+  }
 }
 
 __device__ __forceinline__ void put_split(unsigned char *hi_base, unsigned char *lo_base, int N, int n, int k, float x) {
@@ -162,7 +195,7 @@ __device__ __forceinline__ void put_split(unsigned char *hi_base, unsigned char 
   if (lo_base) *reinterpret_cast<__half *>(lo_base + b_off(N, n, k)) = l;
 }
 
-__global__ void __launch_bounds__(TILE, 4) rollout_tc_kernel(const __grid_constant__ RolloutParams p) {
+__global__ void __launch_bounds__(TILE, 8) rollout_tc_kernel(const __grid_constant__ RolloutParams p, const __grid_constant__ TcEpilogue ep) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) unsigned long long mma_bar;
   __shared__ uint32_t tmem_base_slot;
@@ -179,15 +212,6 @@ __global__ void __launch_bounds__(TILE, 4) rollout_tc_kernel(const __grid_consta
       put_split(smem + OFF_B1A, smem + OFF_B1B, 32, n, k, w);
       put_split(smem + OFF_B1A, nullptr, 32, n, 8 + k, w);
     }
-    if (tid < 32) {
-      const float b = __fmul_rn(th[192 + tid], TANH_SCALE);  // b1 -> K slot 6 (the input carries 1.0 there)
-      put_split(smem + OFF_B1A, smem + OFF_B1B, 32, tid, 6, b);
-      put_split(smem + OFF_B1A, nullptr, 32, tid, 8 + 6, b);
-      const float b2 = __fmul_rn(th[224 + 1024 + tid], TANH_SCALE);  // b2 -> bias chunk: k = 0 hi, k = 1 lo
-      const __half h = __float2half_rn(b2);
-      *reinterpret_cast<__half *>(smem + OFF_B2B + b_off(32, tid, 0)) = h;
-      *reinterpret_cast<__half *>(smem + OFF_B2B + b_off(32, tid, 1)) = __float2half_rn(__fsub_rn(b2, __half2float(h)));
-    }
     for (int i = tid; i < 32 * 32; i += TILE) {  // layer 2
       const int k = i >> 5, n = i & 31;
       put_split(smem + OFF_B2H, smem + OFF_B2L, 32, n, k, __fmul_rn(th[224 + i], TANH_SCALE));
@@ -195,12 +219,6 @@ __global__ void __launch_bounds__(TILE, 4) rollout_tc_kernel(const __grid_consta
     for (int i = tid; i < 32 * 4; i += TILE) {  // layer 3 (linear output, no scale)
       const int k = i >> 2, n = i & 3;
       put_split(smem + OFF_B3H, smem + OFF_B3L, 16, n, k, th[1280 + i]);
-    }
-    if (tid < 4) {
-      const float b3 = th[1408 + tid];
-      const __half h = __float2half_rn(b3);
-      *reinterpret_cast<__half *>(smem + OFF_B3B + b_off(16, tid, 0)) = h;
-      *reinterpret_cast<__half *>(smem + OFF_B3B + b_off(16, tid, 1)) = __float2half_rn(__fsub_rn(b3, __half2float(h)));
     }
   }
   const uint32_t bar = smem_u32(&mma_bar);
@@ -221,11 +239,6 @@ __global__ void __launch_bounds__(TILE, 4) rollout_tc_kernel(const __grid_consta
 
   const uint32_t sb = smem_u32(smem);
   constexpr uint32_t ID32 = idesc(128, 32), ID16 = idesc(128, 16);
-
-  {  // constant bias chunk: k = 0, 1 are 1.0 (hi and lo of the bias), the rest 0
-    uint32_t ones[8] = {0x3C003C00u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-    tmem_st8(lane_base + COL_ONES, ones);
-  }
 
   // ---- rollout bookkeeping (rollout.cuh, R = 1) ----
   const long long total = (long long)p.B * p.n_local;
@@ -264,13 +277,13 @@ __global__ void __launch_bounds__(TILE, 4) rollout_tc_kernel(const __grid_consta
     u0 = u0 < p.lo0 ? p.lo0 : (u0 > p.hi0 ? p.hi0 : u0);  // enforceConstraints
     u1 = u1 < p.lo1 ? p.lo1 : (u1 > p.hi1 ? p.hi1 : u1);
 
-    // ---- layer 1: a = [roll, u_x, u_y, yaw rate, steering, throttle, 1 (bias), 0] as [a_hi | a_lo], one K = 16 chunk ----
+    // ---- layer 1: a = [roll, u_x, u_y, yaw rate, steering, throttle, 0, 0] as [a_hi | a_lo], one K = 16 chunk ----
     {
       uint32_t a[8];
       split2(s[3], s[4], a[0], a[4]);
       split2(s[5], s[6], a[1], a[5]);
       split2(u0, u1, a[2], a[6]);
-      a[3] = 0x00003C00u;  // (1.0, 0)
+      a[3] = 0u;
       a[7] = 0u;
       tmem_st8(lane_base + COL_A, a);
     }
@@ -295,7 +308,7 @@ __global__ void __launch_bounds__(TILE, 4) rollout_tc_kernel(const __grid_consta
     phase ^= 1u;
     fence_after();
 
-    // ---- layers 2 and 3: tanh epilogue -> hi / lo activations back into TMEM -> 7 MMAs each ----
+    // ---- layers 2 and 3: tanh epilogue -> hi / lo activations back into TMEM -> 6 MMAs each ----
 #pragma unroll
     for (int layer = 0; layer < 2; layer++) {
       {
@@ -303,11 +316,11 @@ __global__ void __launch_bounds__(TILE, 4) rollout_tc_kernel(const __grid_consta
         uint32_t h[16];
         tmem_ld16(lane_base + COL_D, v);
         wait_ld();
-        activate16(v, h);
+        activate16(v, layer == 0 ? ep.eb1 : ep.eb2, h);
         tmem_st16(lane_base + COL_A, h);
         tmem_ld16(lane_base + COL_D + 16, v);
         wait_ld();
-        activate16(v, h);
+        activate16(v, (layer == 0 ? ep.eb1 : ep.eb2) + 16, h);
         tmem_st16(lane_base + COL_A + 16, h);
       }
       wait_st();
@@ -319,9 +332,7 @@ __global__ void __launch_bounds__(TILE, 4) rollout_tc_kernel(const __grid_consta
           const int N = layer == 0 ? 32 : 16;
           const uint32_t id = layer == 0 ? ID32 : ID16;
           const uint32_t bh = sb + (layer == 0 ? OFF_B2H : OFF_B3H), bl = sb + (layer == 0 ? OFF_B2L : OFF_B3L);
-          const uint32_t bb = sb + (layer == 0 ? OFF_B2B : OFF_B3B);
-          mma_ts(tmem + COL_D, tmem + COL_ONES, chunk_desc(bb, N, 0), id, 0u);        // bias
-          mma_ts(tmem + COL_D, tmem + COL_A + 8, chunk_desc(bh, N, 0), id, 1u);       // lo(0..15)  x W_hi
+          mma_ts(tmem + COL_D, tmem + COL_A + 8, chunk_desc(bh, N, 0), id, 0u);       // lo(0..15)  x W_hi
           mma_ts(tmem + COL_D, tmem + COL_A + 24, chunk_desc(bh, N, 1), id, 1u);      // lo(16..31) x W_hi
           mma_ts(tmem + COL_D, tmem + COL_A + 0, chunk_desc(bl, N, 0), id, 1u);       // hi(0..15)  x W_lo
           mma_ts(tmem + COL_D, tmem + COL_A + 16, chunk_desc(bl, N, 1), id, 1u);      // hi(16..31) x W_lo
@@ -353,7 +364,7 @@ __global__ void __launch_bounds__(TILE, 4) rollout_tc_kernel(const __grid_consta
     s[1] = fmaf(d1, p.dt, s[1]);
     s[2] = fmaf(d2, p.dt, s[2]);
 #pragma unroll
-    for (int k = 0; k < 4; k++) s[3 + k] = fmaf(o[k], p.dt, s[3 + k]);
+    for (int k = 0; k < 4; k++) s[3 + k] = fmaf(__fadd_rn(o[k], ep.b3[k]), p.dt, s[3 + k]);
     if (fabsf(s[3]) >= 1.57f) crash = 1;  // getCrash, PI/costs.cu:301-305
   }
 
@@ -375,10 +386,16 @@ __global__ void __launch_bounds__(TILE, 4) rollout_tc_kernel(const __grid_consta
 
 }  // namespace tc
 
-cudaError_t launch_rollout_nn32_tc(const RolloutParams &p, cudaStream_t st) {
+cudaError_t launch_rollout_nn32_tc(const RolloutParams &p, cudaStream_t st, const float *host_theta_t) {
   const long long total = (long long)p.B * p.n_local;
   const unsigned grid = (unsigned)((total + tc::TILE - 1) / tc::TILE);
-  tc::rollout_tc_kernel<<<grid, tc::TILE, tc::SMEM_PAD_BYTES, st>>>(p);
+  tc::TcEpilogue ep;
+  for (int j = 0; j < 32; j++) {  // theta_t: Wt1[6][32] b1[32] Wt2[32][32] b2[32] Wt3[32][4] b3[4]
+    ep.eb1[j] = (float)std::exp(2.0 * (double)host_theta_t[192 + j]);
+    ep.eb2[j] = (float)std::exp(2.0 * (double)host_theta_t[1248 + j]);
+  }
+  for (int j = 0; j < 4; j++) ep.b3[j] = host_theta_t[1408 + j];
+  tc::rollout_tc_kernel<<<grid, tc::TILE, tc::SMEM_PAD_BYTES, st>>>(p, ep);
   return cudaGetLastError();
 }
 

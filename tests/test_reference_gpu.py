@@ -74,7 +74,7 @@ def test_nn_spread_weights_three_way(models, costmap, gamma):
     state, U = top_state(4.0), straight_controls(100)
     want = reference_run(ref.REF_NN_1920, models["autorally_nnet_theta"], costmap, cp, state, U, gamma=gamma)
     assert want["normalizer"] > (15 if gamma > 0.1 else 150)
-    for variant in (2, 7, 9):
+    for variant in (2, 7, 9, 10):
         got = cuda_run("nn", models, costmap, cp, 1920, state, U, want["eps"], gamma=gamma, variant=variant)
         compare(got, want, 100, "cuda (variant %d) vs reference" % variant)
     o = make_oracle("nn", models, costmap, cp).compute_control(state, U, HIST, NU, want["eps"], gamma=gamma, threads=8)
