@@ -135,10 +135,17 @@ int resolve_variant(const mppi_ctx *c) {
   if (c->cfg.dynamics == MPPI_DYNAMICS_BF) return MPPI_ROLLOUT_THREAD1;
   if (c->net_kind == 64) return MPPI_ROLLOUT_THREAD1;
   if (v == MPPI_ROLLOUT_AUTO) {
-    // Measured on B200 (profiles/exp_lat_r01.txt): one rollout per half-warp wins up to 32768 rollouts (431 us vs
-    // 537 us for the two-rollouts-per-thread kernel), loses at 65536 (838 us vs 630 us).
-    if (total <= 40960) v = MPPI_ROLLOUT_HALF16;
-    else v = MPPI_ROLLOUT_THREAD2;
+    // Measured on B200 (profiles/exp_tc_r01.txt, rollout kernel only): one rollout per half-warp wins up to 16384 rollouts
+    // (233 us vs 280 us for the tensor-core kernel), loses from 32768 (434 us vs 335 us); the FFMA2 kernel (THREAD2) is
+    // slower than the tensor-core kernel at every size (1M rollouts: 7.2 ms vs 4.0 ms) and stays as a selectable variant.
+    if (total <= 24576) v = MPPI_ROLLOUT_HALF16;
+    else v = MPPI_ROLLOUT_TENSOR;
+  }
+  if (v == MPPI_ROLLOUT_TENSOR) {
+    // the tensor-core kernel folds the hidden-layer biases into its exponentials as 2^(2 log2(e) b) = e^(2b) (rollout_tc.cu):
+    // biases beyond +-40 would leave the FP32 range, so such a network runs on the FFMA2 kernel instead
+    for (int j = 0; j < 32 && c->theta_t.size() >= 1412; j++)
+      if (!(std::fabs(c->theta_t[192 + j]) < 40.0f) || !(std::fabs(c->theta_t[1248 + j]) < 40.0f)) v = MPPI_ROLLOUT_THREAD2;
   }
   if (v == MPPI_ROLLOUT_CONST1) v = MPPI_ROLLOUT_THREAD2;  // constant-bank weights measured no faster (profiles/microbench_r01.txt)
   return v;

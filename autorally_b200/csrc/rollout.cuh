@@ -28,9 +28,17 @@ __device__ __forceinline__ float costmap_lookup(const DevCostParams &cp, cudaTex
   return tex2D<float>(tex, __fdiv_rn(uu, ww), __fdiv_rn(vv, ww));
 }
 
-__device__ __forceinline__ StepCostParts step_cost_parts(const DevCostParams &cp, cudaTextureObject_t tex, float x, float y,
-                                                         float yaw, float vx, float vy, float u0, float u1, float du0,
-                                                         float du1, float nu0, float nu1) {
+// The two costmap fetches of the track cost (:359-380): front / back of the car with the fast intrinsics the reference
+// uses.  Separate from the rest so that a kernel can issue them early and consume the texels later.
+__device__ __forceinline__ void track_lookups(const DevCostParams &cp, cudaTextureObject_t tex, float x, float y, float yaw,
+                                              float &front, float &back) {
+  const float cy = __cosf(yaw), sy = __sinf(yaw);
+  front = costmap_lookup(cp, tex, fmaf(0.5f, cy, x), fmaf(0.5f, sy, y));
+  back = costmap_lookup(cp, tex, fmaf(-0.5f, cy, x), fmaf(-0.5f, sy, y));
+}
+
+__device__ __forceinline__ StepCostParts step_cost_from_lookups(const DevCostParams &cp, float front, float back, float vx, float vy,
+                                                                float u0, float u1, float du0, float du1, float nu0, float nu1) {
   StepCostParts r;
   // control cost (:307-313)
   float control = 0.0f;
@@ -38,10 +46,7 @@ __device__ __forceinline__ StepCostParts step_cost_parts(const DevCostParams &cp
     control = __fadd_rn(control, __fdiv_rn(__fmul_rn(__fmul_rn(cp.steering_coeff, du0), __fsub_rn(u0, du0)), __fmul_rn(nu0, nu0)));
     control = __fadd_rn(control, __fdiv_rn(__fmul_rn(__fmul_rn(cp.throttle_coeff, du1), __fsub_rn(u1, du1)), __fmul_rn(nu1, nu1)));
   }
-  // track cost (:359-393): front / back of the car with the fast intrinsics the reference uses
-  const float cy = __cosf(yaw), sy = __sinf(yaw);
-  const float front = costmap_lookup(cp, tex, fmaf(0.5f, cy, x), fmaf(0.5f, sy, y));
-  const float back = costmap_lookup(cp, tex, fmaf(-0.5f, cy, x), fmaf(-0.5f, sy, y));
+  // track cost (:381-393)
   const float track = __fmul_rn(__fadd_rn(fabsf(front), fabsf(back)), 0.5f);  // "/2.0" in double is exact
   r.track = (fabsf(track) < cp.track_slop) ? 0.0f : __fmul_rn(cp.track_coeff, track);
   r.boundary = (front >= cp.boundary_threshold || back >= cp.boundary_threshold);
@@ -60,17 +65,30 @@ __device__ __forceinline__ StepCostParts step_cost_parts(const DevCostParams &cp
   return r;
 }
 
+__device__ __forceinline__ StepCostParts step_cost_parts(const DevCostParams &cp, cudaTextureObject_t tex, float x, float y,
+                                                         float yaw, float vx, float vy, float u0, float u1, float du0,
+                                                         float du1, float nu0, float nu1) {
+  float front, back;
+  track_lookups(cp, tex, x, y, yaw, front, back);
+  return step_cost_from_lookups(cp, front, back, vx, vy, u0, u1, du0, du1, nu0, nu1);
+}
+
+// computeCost given the parts: the crash flag is sticky, the boundary hit is charged in the same step (:396-409)
+__device__ __forceinline__ float running_cost_from_parts(const DevCostParams &cp, const StepCostParts &c, int &crash) {
+  if (c.boundary) crash = 1;
+  const float crash_cost = crash > 0 ? cp.crash_cost_on : 0.0f;  // (:328-335, :402)
+  float cost = __fadd_rn(__fadd_rn(__fadd_rn(c.pre, crash_cost), c.track), c.stab);
+  if (cost > 1e12f || isnan(cost)) cost = 1e12f;
+  return cost;
+}
+
 // MPPICosts::computeCost: the track cost runs before the crash cost, so a boundary hit is charged in the same
 // step; `crash` is sticky.
 __device__ __forceinline__ float running_cost_step(const DevCostParams &cp, cudaTextureObject_t tex,
                                                    const float (&s)[S_DIM], float u0, float u1, float du0,
                                                    float du1, float nu0, float nu1, int &crash) {
   const StepCostParts c = step_cost_parts(cp, tex, s[0], s[1], s[2], s[4], s[5], u0, u1, du0, du1, nu0, nu1);
-  if (c.boundary) crash = 1;
-  const float crash_cost = crash > 0 ? cp.crash_cost_on : 0.0f;  // (:328-335, :402)
-  float cost = __fadd_rn(__fadd_rn(__fadd_rn(c.pre, crash_cost), c.track), c.stab);
-  if (cost > 1e12f || isnan(cost)) cost = 1e12f;
-  return cost;
+  return running_cost_from_parts(cp, c, crash);
 }
 
 // One thread owns DYN::R consecutive rollouts.  Grid covers B * n_local rollouts; n_local is a

@@ -39,6 +39,10 @@
 namespace mppi {
 namespace tc {
 
+#ifndef TC_EXP
+#define TC_EXP 0  // timing experiments only (tools/exp_tc_parts.sh); 0 = the product kernel
+#endif
+
 constexpr int TILE = 128;         // rollouts per CTA = TMEM lanes
 constexpr int TMEM_COLS = 64;     // allocation (power of two); 8 CTAs per SM
 constexpr int COL_D = 0;          // accumulator, 32 columns
@@ -63,15 +67,13 @@ __device__ __forceinline__ int b_off(int N, int n, int k) { return ((k >> 3) * (
 
 // SM100 shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp): start >> 4 [0,14), LBO >> 4 [16,30) = byte
 // distance between the two 16-byte K halves, SBO >> 4 [32,46) = byte distance between 8-row groups, version 1 [46,48),
-// layout type 0 = no swizzle [61,64).
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, int N) {
+// layout type 0 = no swizzle [61,64).  `base_lo` = (shared address of the B block) >> 4; everything else is a constant.
+__device__ __forceinline__ uint64_t chunk_desc(uint32_t base_lo, int off, int N, int chunk) {
   const uint32_t lbo = (uint32_t)(N >> 3) * 128u, sbo = 128u;
-  const uint32_t lo = ((saddr & 0x3FFFFu) >> 4) | ((lbo >> 4) << 16);
+  const uint32_t lo = base_lo + (((uint32_t)off + (uint32_t)chunk * 2u * lbo) >> 4) + ((lbo >> 4) << 16);  // one K = 16 chunk = two core-matrix columns
   const uint32_t hi = (sbo >> 4) | (1u << 14);
   return ((uint64_t)hi << 32) | lo;
 }
-// one K = 16 chunk = two core-matrix columns
-__device__ __forceinline__ uint64_t chunk_desc(uint32_t saddr, int N, int chunk) { return make_desc(saddr + (uint32_t)chunk * 2u * (uint32_t)(N >> 3) * 128u, N); }
 
 // instruction descriptor: D = F32 [4,6), A = B = F16 (0), both K-major, N >> 3 [17,23), M >> 4 [24,29)
 __host__ __device__ constexpr uint32_t idesc(int M, int N) { return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
@@ -93,13 +95,14 @@ __device__ __forceinline__ void wait_ld() { asm volatile("tcgen05.wait::ld.sync.
 
 // bounded: a mis-programmed MMA must end as wrong numbers (caught by the parity tests), never as a hung GPU
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+  if (TC_EXP == 3 || TC_EXP == 4) return true;
   uint32_t done = 0;
 #pragma unroll 1
-  for (int spin = 0; spin < (1 << 22); spin++) {
+  for (int spin = 0; spin < (1 << 18); spin++) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
         : "=r"(done)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(20000u)  // suspend-time hint (ns): sleep in hardware instead of spinning on issue slots
         : "memory");
     if (done) return true;
   }
@@ -153,8 +156,13 @@ struct TcEpilogue {
 // tanh(x + b) for four neurons; x already scaled by 2 log2(e), eb = 2^(scaled bias).  One MUFU.RCP for all four.
 __device__ __forceinline__ void tanh4(float x0, float x1, float x2, float x3, float2 eb01, float2 eb23, float2 &y01, float2 &y23) {
   const float2 one = make_float2(1.0f, 1.0f);
+#if TC_EXP == 2
+  float2 d01 = __ffma2_rn(make_float2(fmaf(x0, x0, 1.0f), fmaf(x1, x1, 1.0f)), eb01, one);
+  float2 d23 = __ffma2_rn(make_float2(fmaf(x2, x2, 1.0f), fmaf(x3, x3, 1.0f)), eb23, one);
+#else
   float2 d01 = __ffma2_rn(make_float2(ex2_approx(x0), ex2_approx(x1)), eb01, one);
   float2 d23 = __ffma2_rn(make_float2(ex2_approx(x2), ex2_approx(x3)), eb23, one);
+#endif
   const float cap = 1073741824.0f;  // 2^30: 1 - 2/d is 1 to the last bit beyond it; keeps d0 d1 d2 d3 finite
   d01.x = fminf(d01.x, cap); d01.y = fminf(d01.y, cap);
   d23.x = fminf(d23.x, cap); d23.y = fminf(d23.y, cap);
@@ -237,7 +245,7 @@ __global__ void __launch_bounds__(TILE, 8) rollout_tc_kernel(const __grid_consta
   const uint32_t tmem = tmem_base_slot;
   const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);  // this warp's 32 TMEM lanes
 
-  const uint32_t sb = smem_u32(smem);
+  const uint32_t sb = (smem_u32(smem) & 0x3FFFFu) >> 4;
   constexpr uint32_t ID32 = idesc(128, 32), ID16 = idesc(128, 16);
 
   // ---- rollout bookkeeping (rollout.cuh, R = 1) ----
@@ -259,11 +267,13 @@ __global__ void __launch_bounds__(TILE, 8) rollout_tc_kernel(const __grid_consta
   float2 *row = reinterpret_cast<float2 *>(p.du) + (size_t)gc * p.T;
   uint32_t phase = 0;
   bool ok = true;
+  float2 e_next = row[0];  // the noise of step i + 1 is requested a whole step ahead (800-byte row stride: every fetch is a DRAM sector)
 
   for (int i = 0; i < p.T; i++) {
     const float2 Ui = U[i];
     // PI/mppi_controller.cu:130-155
-    const float2 e = row[i];
+    const float2 e = e_next;
+    if (i + 1 < p.T) e_next = row[i + 1];
     float du0, du1, u0, u1;
     if (noise_free || i < p.opt_delay) {
       du0 = 0.0f; du1 = 0.0f; u0 = Ui.x; u1 = Ui.y;
@@ -277,6 +287,10 @@ __global__ void __launch_bounds__(TILE, 8) rollout_tc_kernel(const __grid_consta
     u0 = u0 < p.lo0 ? p.lo0 : (u0 > p.hi0 ? p.hi0 : u0);  // enforceConstraints
     u1 = u1 < p.lo1 ? p.lo1 : (u1 > p.hi1 ? p.hi1 : u1);
 
+    // the two costmap texels of this step's running cost are requested now and consumed after the layer-1 MMAs are issued
+    float front = 0.0f, back = 0.0f;
+    if (i > 0 && TC_EXP != 1) track_lookups(p.cp, p.tex, s[0], s[1], s[2], front, back);
+
     // ---- layer 1: a = [roll, u_x, u_y, yaw rate, steering, throttle, 0, 0] as [a_hi | a_lo], one K = 16 chunk ----
     {
       uint32_t a[8];
@@ -289,19 +303,19 @@ __global__ void __launch_bounds__(TILE, 8) rollout_tc_kernel(const __grid_consta
     }
     wait_st();
     fence_before();
-    __syncthreads();
-    if (warp == 0) {
+    if (TC_EXP != 4) __syncthreads();
+    if (warp == 0 && TC_EXP != 3 && TC_EXP != 4) {
       if (tid == 0) {
         fence_after();
-        mma_ts(tmem + COL_D, tmem + COL_A, chunk_desc(sb + OFF_B1A, 32, 0), ID32, 0u);
-        mma_ts(tmem + COL_D, tmem + COL_A, chunk_desc(sb + OFF_B1B, 32, 0), ID32, 1u);
+        mma_ts(tmem + COL_D, tmem + COL_A, chunk_desc(sb, OFF_B1A, 32, 0), ID32, 0u);
+        mma_ts(tmem + COL_D, tmem + COL_A, chunk_desc(sb, OFF_B1B, 32, 0), ID32, 1u);
         mma_commit(bar);
       }
       __syncwarp();
     }
     // the running cost of this step overlaps the MMA round trip (state before the dynamics, PI/mppi_controller.cu:162-165)
-    if (i > 0) {
-      const float c = running_cost_step(p.cp, p.tex, s, u0, u1, du0, du1, p.nu0, p.nu1, crash);
+    if (i > 0 && TC_EXP != 1) {
+      const float c = running_cost_from_parts(p.cp, step_cost_from_lookups(p.cp, front, back, s[4], s[5], u0, u1, du0, du1, p.nu0, p.nu1), crash);
       running = (float)((double)running + (double)__fsub_rn(c, running) * p.inv_step[i]);
     }
     ok = mbar_wait(bar, phase) && ok;
@@ -325,19 +339,19 @@ __global__ void __launch_bounds__(TILE, 8) rollout_tc_kernel(const __grid_consta
       }
       wait_st();
       fence_before();
-      __syncthreads();
-      if (warp == 0) {
+      if (TC_EXP != 4) __syncthreads();
+      if (warp == 0 && TC_EXP != 3 && TC_EXP != 4) {
         if (tid == 0) {
           fence_after();
           const int N = layer == 0 ? 32 : 16;
           const uint32_t id = layer == 0 ? ID32 : ID16;
-          const uint32_t bh = sb + (layer == 0 ? OFF_B2H : OFF_B3H), bl = sb + (layer == 0 ? OFF_B2L : OFF_B3L);
-          mma_ts(tmem + COL_D, tmem + COL_A + 8, chunk_desc(bh, N, 0), id, 0u);       // lo(0..15)  x W_hi
-          mma_ts(tmem + COL_D, tmem + COL_A + 24, chunk_desc(bh, N, 1), id, 1u);      // lo(16..31) x W_hi
-          mma_ts(tmem + COL_D, tmem + COL_A + 0, chunk_desc(bl, N, 0), id, 1u);       // hi(0..15)  x W_lo
-          mma_ts(tmem + COL_D, tmem + COL_A + 16, chunk_desc(bl, N, 1), id, 1u);      // hi(16..31) x W_lo
-          mma_ts(tmem + COL_D, tmem + COL_A + 0, chunk_desc(bh, N, 0), id, 1u);       // hi x W_hi
-          mma_ts(tmem + COL_D, tmem + COL_A + 16, chunk_desc(bh, N, 1), id, 1u);
+          const int bh = layer == 0 ? OFF_B2H : OFF_B3H, bl = layer == 0 ? OFF_B2L : OFF_B3L;
+          mma_ts(tmem + COL_D, tmem + COL_A + 8, chunk_desc(sb, bh, N, 0), id, 0u);       // lo(0..15)  x W_hi
+          mma_ts(tmem + COL_D, tmem + COL_A + 24, chunk_desc(sb, bh, N, 1), id, 1u);      // lo(16..31) x W_hi
+          mma_ts(tmem + COL_D, tmem + COL_A + 0, chunk_desc(sb, bl, N, 0), id, 1u);       // hi(0..15)  x W_lo
+          mma_ts(tmem + COL_D, tmem + COL_A + 16, chunk_desc(sb, bl, N, 1), id, 1u);      // hi(16..31) x W_lo
+          mma_ts(tmem + COL_D, tmem + COL_A + 0, chunk_desc(sb, bh, N, 0), id, 1u);       // hi x W_hi
+          mma_ts(tmem + COL_D, tmem + COL_A + 16, chunk_desc(sb, bh, N, 1), id, 1u);
           mma_commit(bar);
         }
         __syncwarp();
@@ -349,7 +363,7 @@ __global__ void __launch_bounds__(TILE, 8) rollout_tc_kernel(const __grid_consta
     }
     // kinematics (PI/neural_net_model.cu:346-355, precise sinf / cosf) while the last layer is in flight
     float sn, cs;
-    sincosf(s[2], &sn, &cs);
+    if (TC_EXP == 5) __sincosf(s[2], &sn, &cs); else sincosf(s[2], &sn, &cs);
     const float d0 = fmaf(cs, s[4], -__fmul_rn(sn, s[5]));
     const float d1 = fmaf(sn, s[4], __fmul_rn(cs, s[5]));
     const float d2 = p.negate_yaw ? -s[6] : s[6];

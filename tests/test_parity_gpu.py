@@ -263,3 +263,73 @@ def test_launch_paths_are_bitwise_equivalent(models, costmap, monkeypatch):
             np.testing.assert_array_equal(b[k], results[0][1][k])
         np.testing.assert_array_equal(c, results[0][2])
     assert not np.array_equal(results[0][0]["U"], results[0][1]["U"])  # fresh noise on the second call
+
+
+# ---- the tensor-core rollout kernel (MPPI_ROLLOUT_TENSOR = 10, rollout_tc.cu; AUTO above 24576 rollouts) ----
+
+@pytest.mark.parametrize("N,T", [(64, 1), (64, 2), (192, 7), (320, 33), (4096, 100)])
+def test_tensor_kernel_ragged_sizes(models, costmap, N, T):
+    """Partial 128-rollout tiles (idle TMEM lanes), single-step horizons, odd multiples of 64."""
+    want, got = run_pair("nn", models, costmap, N, T=T, seed=N + T, variant=10)
+    check_pair(want, got)
+
+
+def test_tensor_kernel_cost_terms_and_opt_delay(models, costmap):
+    over = dict(steering_coeff=0.4, throttle_coeff=0.2, track_slop=0.05, l1_cost=True, max_slip_ang=0.4)
+    want, got = run_pair("nn", models, costmap, 512, T=50, cp_over=over, opt_delay=3, variant=10)
+    check_pair(want, got)
+
+
+def test_tensor_kernel_tiles_straddling_controllers(models, costmap):
+    """192 rollouts per controller: every second 128-rollout tile holds rollouts of two controllers."""
+    from autorally_b200.params import ellipse_states
+    cp = cost_params_for(costmap)
+    B, N, T = 6, 192, 100
+    states = ellipse_states(B)
+    eps = np.random.default_rng(19).standard_normal((B, N, T, 2)).astype(np.float32)
+    U = np.broadcast_to(warm_controls(T), (B, T, 2)).copy()
+    with make_context("nn", models, costmap, cp, N, num_controllers=B, variant=10) as ctx:
+        ctx.set_noise(eps)
+        got = ctx.compute_control(states, U)
+        costs = ctx.rollout_costs()
+        assert ctx.resolved_variant() == 10
+    o = make_oracle("nn", models, costmap, cp)
+    for b in range(B):
+        want = o.compute_control(states[b], U[b], np.zeros(4), NU, eps[b][None], threads=8)
+        check_costs(costs[b], want["costs"], T)
+        assert rel_err(got["U"][b], want["U"]).max() < 1e-4
+
+
+def test_auto_picks_the_tensor_kernel_at_65536_and_matches_oracle(models, costmap):
+    want, got = run_pair("nn", models, costmap, 65536, speed=4.0, scenario="top", seed=3)
+    check_pair(want, got)
+    cp = cost_params_for(costmap)
+    with make_context("nn", models, costmap, cp, 65536) as ctx:
+        assert ctx.resolved_variant() == 10
+    with make_context("nn", models, costmap, cp, 1920) as ctx:
+        assert ctx.resolved_variant() == 9
+
+
+def test_1m_rollouts_tensor_and_ffma2_kernels_agree(models, costmap):
+    """BASELINE config 4 at full size (1M rollouts x 100 steps, Philox noise): the tensor-core kernel and the FP32 FFMA2
+    kernel are two independent implementations of the same rollouts; same seed => same noise => same costs and controls."""
+    cp = cost_params_for(costmap)
+    N, T = 1048576, 100
+    state, U = top_state(4.0), straight_controls(T)
+    res = {}
+    for variant in (10, 2):
+        with make_context("nn", models, costmap, cp, N, variant=variant) as ctx:
+            ctx.use_sampler()
+            ctx.seed(1234, 0)
+            out = ctx.compute_control(state, U)
+            out["costs"] = ctx.rollout_costs()
+            out["crash"] = ctx.rollout_crash()
+            assert ctx.resolved_variant() == variant
+            res[variant] = out
+    a, b = res[10], res[2]
+    assert (a["crash"] == b["crash"]).mean() > 0.999
+    check_costs(a["costs"], b["costs"], T, min_ok=0.995)
+    assert abs(a["baseline"] - b["baseline"]) <= 1e-4 * (1 + abs(b["baseline"]))
+    assert rel_err(a["normalizer"], b["normalizer"]).max() < 1e-3
+    assert rel_err(a["U"], b["U"]).max() < 1e-4
+    assert rel_err(a["state_solution"], b["state_solution"]).max() < 1e-4
