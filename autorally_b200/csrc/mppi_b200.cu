@@ -142,10 +142,13 @@ int resolve_variant(const mppi_ctx *c) {
     else v = MPPI_ROLLOUT_TENSOR;
   }
   if (v == MPPI_ROLLOUT_TENSOR) {
-    // the tensor-core kernel folds the hidden-layer biases into its exponentials as 2^(2 log2(e) b) = e^(2b) (rollout_tc.cu):
-    // biases beyond +-40 would leave the FP32 range, so such a network runs on the FFMA2 kernel instead
-    for (int j = 0; j < 32 && c->theta_t.size() >= 1412; j++)
-      if (!(std::fabs(c->theta_t[192 + j]) < 40.0f) || !(std::fabs(c->theta_t[1248 + j]) < 40.0f)) v = MPPI_ROLLOUT_THREAD2;
+    // the tensor-core kernel folds the hidden-layer biases into its exponentials as e^(2 b1) and e^(2 (b2 + rowsum W2))
+    // (rollout_tc.cu): beyond +-40 these would leave the FP32 range, so such a network runs on the FFMA2 kernel instead
+    for (int j = 0; j < 32 && c->theta_t.size() >= 1412; j++) {
+      double s2 = c->theta_t[1248 + j];
+      for (int k = 0; k < 32; k++) s2 += (double)c->theta_t[224 + k * 32 + j];
+      if (!(std::fabs(c->theta_t[192 + j]) < 40.0f) || !(std::fabs(s2) < 40.0)) v = MPPI_ROLLOUT_THREAD2;
+    }
   }
   if (v == MPPI_ROLLOUT_CONST1) v = MPPI_ROLLOUT_THREAD2;  // constant-bank weights measured no faster (profiles/microbench_r01.txt)
   return v;

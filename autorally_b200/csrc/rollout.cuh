@@ -37,31 +37,47 @@ __device__ __forceinline__ void track_lookups(const DevCostParams &cp, cudaTextu
   back = costmap_lookup(cp, tex, fmaf(-0.5f, cy, x), fmaf(-0.5f, sy, y));
 }
 
-__device__ __forceinline__ StepCostParts step_cost_from_lookups(const DevCostParams &cp, float front, float back, float vx, float vy,
-                                                                float u0, float u1, float du0, float du1, float nu0, float nu1) {
-  StepCostParts r;
-  // control cost (:307-313)
+// control cost (:307-313); depends on the controls only
+__device__ __forceinline__ float cost_control_part(const DevCostParams &cp, float u0, float u1, float du0, float du1, float nu0, float nu1) {
   float control = 0.0f;
   if (cp.has_control_cost) {
     control = __fadd_rn(control, __fdiv_rn(__fmul_rn(__fmul_rn(cp.steering_coeff, du0), __fsub_rn(u0, du0)), __fmul_rn(nu0, nu0)));
     control = __fadd_rn(control, __fdiv_rn(__fmul_rn(__fmul_rn(cp.throttle_coeff, du1), __fsub_rn(u1, du1)), __fmul_rn(nu1, nu1)));
   }
-  // track cost (:381-393)
-  const float track = __fmul_rn(__fadd_rn(fabsf(front), fabsf(back)), 0.5f);  // "/2.0" in double is exact
-  r.track = (fabsf(track) < cp.track_slop) ? 0.0f : __fmul_rn(cp.track_coeff, track);
-  r.boundary = (front >= cp.boundary_threshold || back >= cp.boundary_threshold);
-  // speed cost (:315-326)
+  return control;
+}
+
+// control cost + speed cost (:315-326): the part summed before the crash cost
+__device__ __forceinline__ float cost_pre_part(const DevCostParams &cp, float control, float vx) {
   const float err = __fsub_rn(vx, cp.desired_speed);
   const float sc = cp.l1_cost ? fabsf(err) : __fmul_rn(err, err);
-  r.pre = __fadd_rn(control, __fmul_rn(cp.speed_coeff, sc));
-  // stabilizing cost (:337-349); the reference compares |u_x| against the double 0.001
+  return __fadd_rn(control, __fmul_rn(cp.speed_coeff, sc));
+}
+
+// track cost from the two texels (:381-393) and whether the boundary was hit
+__device__ __forceinline__ float cost_track_part(const DevCostParams &cp, float front, float back, bool &boundary) {
+  const float track = __fmul_rn(__fadd_rn(fabsf(front), fabsf(back)), 0.5f);  // "/2.0" in double is exact
+  boundary = (front >= cp.boundary_threshold || back >= cp.boundary_threshold);
+  return (fabsf(track) < cp.track_slop) ? 0.0f : __fmul_rn(cp.track_coeff, track);
+}
+
+// stabilizing cost (:337-349); the reference compares |u_x| against the double 0.001
+__device__ __forceinline__ float cost_stab_part(const DevCostParams &cp, float vx, float vy) {
   float stab = 0.0f;
   if (fabsf(vx) >= 0.001f) {  // |u_x| > 0.001 (double)  <=>  |u_x| >= 0.001f because 0.001f > 0.001
     const float slip = -atanf(__fdiv_rn(vy, fabsf(vx)));
     stab = __fmul_rn(cp.slip_penalty, __fmul_rn(slip, slip));
     if (fabsf(slip) > cp.max_slip_ang) stab = __fadd_rn(stab, cp.crash_coeff);
   }
-  r.stab = stab;
+  return stab;
+}
+
+__device__ __forceinline__ StepCostParts step_cost_from_lookups(const DevCostParams &cp, float front, float back, float vx, float vy,
+                                                                float u0, float u1, float du0, float du1, float nu0, float nu1) {
+  StepCostParts r;
+  r.track = cost_track_part(cp, front, back, r.boundary);
+  r.pre = cost_pre_part(cp, cost_control_part(cp, u0, u1, du0, du1, nu0, nu1), vx);
+  r.stab = cost_stab_part(cp, vx, vy);
   return r;
 }
 

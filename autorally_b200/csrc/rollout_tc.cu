@@ -19,7 +19,9 @@
 // The tanh epilogue is what remains on the CUDA cores, and the MUFU unit (16 results/clk/SM) is its bottleneck, so it
 // is written to need as few MUFU results as possible.  The hidden layers' weights are pre-multiplied by 2 log2(e), and
 // the bias is folded into the exponential: 2^(x' + b') = 2^x' * 2^b' with 2^b' a kernel constant, so
-//   tanh(x + b) = 1 - 2 / (2^x' 2^b' + 1):   MUFU.EX2, one FFMA for "* 2^b' + 1", a reciprocal, one FFMA;
+//   tanh(x + b) = 1 - 2 r,  r = 1 / (2^x' 2^b' + 1):   MUFU.EX2, one FFMA for "* 2^b' + 1", a reciprocal;
+// the affine map 1 - 2r is folded into the NEXT layer (W y + b = (b + W 1) - 2 W r: the next layer's B matrix is -2 W,
+// its bias b + rowsum(W)), so the activations that travel through tensor memory are the r themselves;
 // and the reciprocals of FOUR neurons share ONE MUFU.RCP (1/(d0 d1 d2 d3) and five packed multiplies; every d is
 // clamped to 2^30, where tanh is 1 to the last bit, so the product cannot overflow): 5 MUFU per 4 neurons, not 8.
 //
@@ -148,13 +150,14 @@ __device__ __forceinline__ void split2(float x0, float x1, uint32_t &hi, uint32_
   lo = *reinterpret_cast<const uint32_t *>(&l);
 }
 
-// Epilogue constants, in the kernel parameter block (constant bank): 2^(2 log2(e) b) per hidden neuron, b3 as is.
+// Epilogue constants, in the kernel parameter block (constant bank): e^(2 b1), e^(2 (b2 + rowsum W2)), b3 + rowsum W3.
 struct TcEpilogue {
   float eb1[32], eb2[32], b3[4];
 };
 
-// tanh(x + b) for four neurons; x already scaled by 2 log2(e), eb = 2^(scaled bias).  One MUFU.RCP for all four.
-__device__ __forceinline__ void tanh4(float x0, float x1, float x2, float x3, float2 eb01, float2 eb23, float2 &y01, float2 &y23) {
+// r = 1 / (2^x eb + 1) for four neurons (tanh(.) = 1 - 2r); x already scaled by 2 log2(e), eb = 2^(scaled bias).
+// One MUFU.RCP for all four.
+__device__ __forceinline__ void recip4(float x0, float x1, float x2, float x3, float2 eb01, float2 eb23, float2 &r01, float2 &r23) {
   const float2 one = make_float2(1.0f, 1.0f);
 #if TC_EXP == 2
   float2 d01 = __ffma2_rn(make_float2(fmaf(x0, x0, 1.0f), fmaf(x1, x1, 1.0f)), eb01, one);
@@ -169,11 +172,8 @@ __device__ __forceinline__ void tanh4(float x0, float x1, float x2, float x3, fl
   const float2 q = __fmul2_rn(d01, d23);                   // (d0 d2, d1 d3)
   const float r = rcp_approx(__fmul_rn(q.x, q.y));         // 1 / (d0 d1 d2 d3)
   const float2 iq = __fmul2_rn(make_float2(r, r), make_float2(q.y, q.x));  // (1 / (d0 d2), 1 / (d1 d3))
-  const float2 i01 = __fmul2_rn(iq, d23);                  // (1 / d0, 1 / d1)
-  const float2 i23 = __fmul2_rn(iq, d01);                  // (1 / d2, 1 / d3)
-  const float2 m2 = make_float2(-2.0f, -2.0f);
-  y01 = __ffma2_rn(m2, i01, one);
-  y23 = __ffma2_rn(m2, i23, one);
+  r01 = __fmul2_rn(iq, d23);                               // (1 / d0, 1 / d1)
+  r23 = __fmul2_rn(iq, d01);                               // (1 / d2, 1 / d3)
 }
 
 __device__ __forceinline__ void split2v(float2 y, uint32_t &hi, uint32_t &lo) {
@@ -190,7 +190,7 @@ __device__ __forceinline__ void activate16(const float (&v)[16], const float *eb
 #pragma unroll
   for (int j = 0; j < 4; j++) {
     float2 y01, y23;
-    tanh4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3], make_float2(eb[4 * j], eb[4 * j + 1]), make_float2(eb[4 * j + 2], eb[4 * j + 3]), y01, y23);
+    recip4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3], make_float2(eb[4 * j], eb[4 * j + 1]), make_float2(eb[4 * j + 2], eb[4 * j + 3]), y01, y23);
     split2v(y01, out[2 * j], out[8 + 2 * j]);
     split2v(y23, out[2 * j + 1], out[8 + 2 * j + 1]);
   }
@@ -220,13 +220,13 @@ __global__ void __launch_bounds__(TILE, 8) rollout_tc_kernel(const __grid_consta
       put_split(smem + OFF_B1A, smem + OFF_B1B, 32, n, k, w);
       put_split(smem + OFF_B1A, nullptr, 32, n, 8 + k, w);
     }
-    for (int i = tid; i < 32 * 32; i += TILE) {  // layer 2
+    for (int i = tid; i < 32 * 32; i += TILE) {  // layer 2 acts on r1: -2 W2 (and the tanh scale)
       const int k = i >> 5, n = i & 31;
-      put_split(smem + OFF_B2H, smem + OFF_B2L, 32, n, k, __fmul_rn(th[224 + i], TANH_SCALE));
+      put_split(smem + OFF_B2H, smem + OFF_B2L, 32, n, k, __fmul_rn(th[224 + i], -2.0f * TANH_SCALE));
     }
-    for (int i = tid; i < 32 * 4; i += TILE) {  // layer 3 (linear output, no scale)
+    for (int i = tid; i < 32 * 4; i += TILE) {  // layer 3 acts on r2: -2 W3 (linear output, no tanh scale)
       const int k = i >> 2, n = i & 3;
-      put_split(smem + OFF_B3H, smem + OFF_B3L, 16, n, k, th[1280 + i]);
+      put_split(smem + OFF_B3H, smem + OFF_B3L, 16, n, k, -2.0f * th[1280 + i]);
     }
   }
   const uint32_t bar = smem_u32(&mma_bar);
@@ -267,11 +267,15 @@ __global__ void __launch_bounds__(TILE, 8) rollout_tc_kernel(const __grid_consta
   float2 *row = reinterpret_cast<float2 *>(p.du) + (size_t)gc * p.T;
   uint32_t phase = 0;
   bool ok = true;
-  float2 e_next = row[0];  // the noise of step i + 1 is requested a whole step ahead (800-byte row stride: every fetch is a DRAM sector)
 
-  for (int i = 0; i < p.T; i++) {
+  // The controls of a step do not depend on the state, so they are prepared one step ahead, inside the wait for the last
+  // layer of the previous step (PI/mppi_controller.cu:130-155 + enforceConstraints).  The noise row has an 800-byte
+  // stride (every fetch is its own DRAM sector) and is requested a whole step before it is used.
+  float2 e_next = row[0];
+  float control_cost;    // control cost of the prepared step (PI/costs.cu:307-313): a function of the controls only
+  uint32_t ua_hi, ua_lo;  // FP16 hi / lo pairs of the clamped controls, ready for the layer-1 operand
+  auto prepare_controls = [&](int i) {
     const float2 Ui = U[i];
-    // PI/mppi_controller.cu:130-155
     const float2 e = e_next;
     if (i + 1 < p.T) e_next = row[i + 1];
     float du0, du1, u0, u1;
@@ -286,17 +290,19 @@ __global__ void __launch_bounds__(TILE, 8) rollout_tc_kernel(const __grid_consta
     if (valid) row[i] = make_float2(u0, u1);  // un-clamped write-back (:153)
     u0 = u0 < p.lo0 ? p.lo0 : (u0 > p.hi0 ? p.hi0 : u0);  // enforceConstraints
     u1 = u1 < p.lo1 ? p.lo1 : (u1 > p.hi1 ? p.hi1 : u1);
+    control_cost = cost_control_part(p.cp, u0, u1, du0, du1, p.nu0, p.nu1);
+    split2(u0, u1, ua_hi, ua_lo);
+  };
+  prepare_controls(0);
+  float front = 0.0f, back = 0.0f;  // costmap texels under the state of the current step (requested one step ahead as well)
 
-    // the two costmap texels of this step's running cost are requested now and consumed after the layer-1 MMAs are issued
-    float front = 0.0f, back = 0.0f;
-    if (i > 0 && TC_EXP != 1) track_lookups(p.cp, p.tex, s[0], s[1], s[2], front, back);
-
+  for (int i = 0; i < p.T; i++) {
     // ---- layer 1: a = [roll, u_x, u_y, yaw rate, steering, throttle, 0, 0] as [a_hi | a_lo], one K = 16 chunk ----
     {
       uint32_t a[8];
       split2(s[3], s[4], a[0], a[4]);
       split2(s[5], s[6], a[1], a[5]);
-      split2(u0, u1, a[2], a[6]);
+      a[2] = ua_hi; a[6] = ua_lo;
       a[3] = 0u;
       a[7] = 0u;
       tmem_st8(lane_base + COL_A, a);
@@ -313,10 +319,15 @@ __global__ void __launch_bounds__(TILE, 8) rollout_tc_kernel(const __grid_consta
       }
       __syncwarp();
     }
-    // the running cost of this step overlaps the MMA round trip (state before the dynamics, PI/mppi_controller.cu:162-165)
+    // The running cost of this step (state before the dynamics, PI/mppi_controller.cu:162-165) is spread over the waits
+    // for the three layers.  Here: control + speed + crash + track, in the reference's summation order (PI/costs.cu:396-409).
+    float cost_acc = 0.0f;
     if (i > 0 && TC_EXP != 1) {
-      const float c = running_cost_from_parts(p.cp, step_cost_from_lookups(p.cp, front, back, s[4], s[5], u0, u1, du0, du1, p.nu0, p.nu1), crash);
-      running = (float)((double)running + (double)__fsub_rn(c, running) * p.inv_step[i]);
+      bool boundary;
+      const float track = cost_track_part(p.cp, front, back, boundary);
+      if (boundary) crash = 1;
+      const float pre = cost_pre_part(p.cp, control_cost, s[4]);
+      cost_acc = __fadd_rn(__fadd_rn(pre, crash > 0 ? p.cp.crash_cost_on : 0.0f), track);
     }
     ok = mbar_wait(bar, phase) && ok;
     phase ^= 1u;
@@ -357,26 +368,38 @@ __global__ void __launch_bounds__(TILE, 8) rollout_tc_kernel(const __grid_consta
         __syncwarp();
       }
       if (layer == 1) break;
+      // second wait: the stabilizing cost (atan of the slip angle), the NaN / 1e12 clamp and the running mean (:162-165)
+      if (i > 0 && TC_EXP != 1) {
+        float c = __fadd_rn(cost_acc, cost_stab_part(p.cp, s[4], s[5]));
+        if (c > 1e12f || isnan(c)) c = 1e12f;
+        running = (float)((double)running + (double)__fsub_rn(c, running) * p.inv_step[i]);
+      }
       ok = mbar_wait(bar, phase) && ok;
       phase ^= 1u;
       fence_after();
     }
-    // kinematics (PI/neural_net_model.cu:346-355, precise sinf / cosf) while the last layer is in flight
-    float sn, cs;
-    if (TC_EXP == 5) __sincosf(s[2], &sn, &cs); else sincosf(s[2], &sn, &cs);
-    const float d0 = fmaf(cs, s[4], -__fmul_rn(sn, s[5]));
-    const float d1 = fmaf(sn, s[4], __fmul_rn(cs, s[5]));
-    const float d2 = p.negate_yaw ? -s[6] : s[6];
+    // third wait: kinematics (PI/neural_net_model.cu:346-355, precise sinf / cosf); x, y, yaw of the next state do not
+    // depend on the network, so they are advanced now and the next step's costmap texels and controls are requested
+    {
+      float sn, cs;
+      if (TC_EXP == 5) __sincosf(s[2], &sn, &cs); else sincosf(s[2], &sn, &cs);
+      const float d0 = fmaf(cs, s[4], -__fmul_rn(sn, s[5]));
+      const float d1 = fmaf(sn, s[4], __fmul_rn(cs, s[5]));
+      const float d2 = p.negate_yaw ? -s[6] : s[6];
+      s[0] = fmaf(d0, p.dt, s[0]);  // incrementState, PI/neural_net_model.cu:334-344
+      s[1] = fmaf(d1, p.dt, s[1]);
+      s[2] = fmaf(d2, p.dt, s[2]);
+    }
+    if (i + 1 < p.T) {
+      if (TC_EXP != 1) track_lookups(p.cp, p.tex, s[0], s[1], s[2], front, back);
+      prepare_controls(i + 1);
+    }
     ok = mbar_wait(bar, phase) && ok;
     phase ^= 1u;
     fence_after();
     float o[4];
     tmem_ld4(lane_base + COL_D, o);
     wait_ld();
-    // incrementState, PI/neural_net_model.cu:334-344
-    s[0] = fmaf(d0, p.dt, s[0]);
-    s[1] = fmaf(d1, p.dt, s[1]);
-    s[2] = fmaf(d2, p.dt, s[2]);
 #pragma unroll
     for (int k = 0; k < 4; k++) s[3 + k] = fmaf(__fadd_rn(o[k], ep.b3[k]), p.dt, s[3 + k]);
     if (fabsf(s[3]) >= 1.57f) crash = 1;  // getCrash, PI/costs.cu:301-305
@@ -404,11 +427,18 @@ cudaError_t launch_rollout_nn32_tc(const RolloutParams &p, cudaStream_t st, cons
   const long long total = (long long)p.B * p.n_local;
   const unsigned grid = (unsigned)((total + tc::TILE - 1) / tc::TILE);
   tc::TcEpilogue ep;
-  for (int j = 0; j < 32; j++) {  // theta_t: Wt1[6][32] b1[32] Wt2[32][32] b2[32] Wt3[32][4] b3[4]
+  // theta_t: Wt1[6][32] b1[32] Wt2[32][32] b2[32] Wt3[32][4] b3[4]; the folded biases are b + rowsum(W) (tanh = 1 - 2r)
+  for (int j = 0; j < 32; j++) {
+    double s2 = host_theta_t[1248 + j];
+    for (int k = 0; k < 32; k++) s2 += (double)host_theta_t[224 + k * 32 + j];
     ep.eb1[j] = (float)std::exp(2.0 * (double)host_theta_t[192 + j]);
-    ep.eb2[j] = (float)std::exp(2.0 * (double)host_theta_t[1248 + j]);
+    ep.eb2[j] = (float)std::exp(2.0 * s2);
   }
-  for (int j = 0; j < 4; j++) ep.b3[j] = host_theta_t[1408 + j];
+  for (int j = 0; j < 4; j++) {
+    double s3 = host_theta_t[1408 + j];
+    for (int k = 0; k < 32; k++) s3 += (double)host_theta_t[1280 + k * 4 + j];
+    ep.b3[j] = (float)s3;
+  }
   tc::rollout_tc_kernel<<<grid, tc::TILE, tc::SMEM_PAD_BYTES, st>>>(p, ep);
   return cudaGetLastError();
 }

@@ -30,6 +30,8 @@ if ROOT not in sys.path:
 
 FLOP_PER_ROLLOUT_STEP_NN = 2756.0  # 2*(6*32+32*32+32*4) + 68 bias adds
 N_ROLLOUTS, T_STEPS = 1920, 100
+# rollout_tc.cu: per 128-rollout tile and timestep 2 MMAs 128x32x16 (layer 1), 6 of 128x32x16, 6 of 128x16x16
+TENSOR_FLOP_ISSUED_PER_ROLLOUT_STEP = 2.0 * (2 * 32 * 16 + 6 * 32 * 16 + 6 * 16 * 16)
 LARGE_ROLLOUTS = 1 << 20           # "large-sample MPPI": 1M rollouts (16384 x 64)
 
 
@@ -218,6 +220,14 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def measured_peaks():
+    """MEASURED_PEAKS.json (driver-written on this pool's B200s) or the profiling guide's fallbacks."""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return json.load(open(path))
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback (B200_PROFILING.md)"}
+
+
 def measure_large(models, costmap, cp, state, U, n_rollouts, r_begin=0, r_count=0, steps=3, fp32_peak=None, hbm_peak=None):
     from tests.common import make_context
     out = {}
@@ -232,6 +242,16 @@ def measure_large(models, costmap, cp, state, U, n_rollouts, r_begin=0, r_count=
         out["rollout_tflops"] = tf
         if fp32_peak:
             out["rollout_frac_of_fp32_peak"] = tf / fp32_peak
+        if out["variant"] == 10:
+            # rollout_tc_kernel: the contraction runs on the tensor pipe (tcgen05, FP16 hi/lo split = 3 passes, K and N padded
+            # to the MMA shapes), so the algorithmic FP32 rate above may exceed the CUDA-core FFMA peak; what the kernel is
+            # bound by is the tanh / split / cost epilogue on the CUDA cores (profiles/ncu_1m_r01t.txt).
+            issued = TENSOR_FLOP_ISSUED_PER_ROLLOUT_STEP * n_local * T_STEPS / (rk / steps * 1e-3) / 1e12
+            peaks = measured_peaks()
+            out.update(kernel="rollout_tc_kernel", tensor_tflops_issued=issued,
+                       tensor_frac_of_measured_dense_16bit_peak=issued / peaks["bf16_tflops"] if peaks.get("bf16_tflops") else None,
+                       note="layer contractions on tcgen05 (A in tensor memory); rollout_tflops counts the 2756 algorithmic "
+                            "FLOP per rollout-step, tensor_tflops_issued the 11264 FLOP the 14 MMAs per tile-step execute")
     return out
 
 
