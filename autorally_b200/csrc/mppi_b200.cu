@@ -200,7 +200,7 @@ cudaError_t launch_noise(mppi_ctx *c, bool pull_inbox = false) {
   sample_noise_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(
       c->d_du, c->n_local, c->r_begin, c->T, c->B, (uint32_t)c->seed, (uint32_t)(c->seed >> 32), c->d_call_counter,
       pull_inbox ? reinterpret_cast<const float4 *>(c->h_inbox_dev) : nullptr, reinterpret_cast<float4 *>(c->d_inbox),
-      c->B * c->inbox_stride / 4);
+      c->B * c->inbox_stride / 4, FastDiv::make((uint32_t)((c->T + 1) / 2)), FastDiv::make((uint32_t)c->n_local));
   return cudaGetLastError();
 }
 

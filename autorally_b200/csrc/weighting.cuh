@@ -38,6 +38,23 @@ __device__ __forceinline__ float2 box_muller(uint32_t xa, uint32_t xb) {
   return make_float2(rad * cs, rad * sn);
 }
 
+// Division of an index below 2^31 by a run-time constant as one multiply-high and a shift (the two divisions by Q and
+// n_local were a quarter of the sampler's instructions): with s = ceil(log2 d), M = ceil(2^(31+s) / d) < 2^32 and
+// n (M d - 2^(31+s)) < 2^(31+s) for every n < 2^31, so (n M) >> (31 + s) is exact.
+struct FastDiv {
+  uint32_t mul, shift;  // mul == 0: divisor 1
+  __host__ static FastDiv make(uint32_t d) {
+    FastDiv f{0u, 0u};
+    if (d <= 1u) return f;
+    uint32_t s = 0;
+    while ((1ull << s) < d) s++;
+    f.mul = (uint32_t)(((1ull << (31 + s)) + d - 1) / d);
+    f.shift = s - 1;  // after the implicit >> 32 of the multiply-high
+    return f;
+  }
+  __device__ __forceinline__ uint32_t div(uint32_t n) const { return mul ? (__umulhi(n, mul) >> shift) : n; }
+};
+
 // `call_ptr` is the device-resident compute-call counter (advanced by finalize_kernel), so a captured
 // CUDA graph replays with a fresh Philox offset every launch.
 //
@@ -48,7 +65,7 @@ __global__ void __launch_bounds__(256) sample_noise_kernel(float *__restrict__ d
                                                             int B, uint32_t seed_lo, uint32_t seed_hi,
                                                             const uint32_t *__restrict__ call_ptr,
                                                             const float4 *__restrict__ inbox_src, float4 *__restrict__ inbox_dst,
-                                                            int inbox_float4s) {
+                                                            int inbox_float4s, FastDiv divQ, FastDiv divN) {
   pdl_trigger();  // the rollout kernel may start fetching its weights now
   if (inbox_src != nullptr && blockIdx.x == 0)
     for (int i = threadIdx.x; i < inbox_float4s; i += blockDim.x) inbox_dst[i] = inbox_src[i];
@@ -60,8 +77,8 @@ __global__ void __launch_bounds__(256) sample_noise_kernel(float *__restrict__ d
   if (total < (1LL << 31)) {
     const unsigned utotal = (unsigned)total, uQ = (unsigned)Q, un = (unsigned)n_local, stride = gridDim.x * blockDim.x;
     for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < utotal; idx += stride) {
-      const unsigned g = idx / uQ, q = idx - g * uQ;
-      const unsigned b = (B == 1) ? 0u : g / un, lr = g - b * un;
+      const unsigned g = divQ.div(idx), q = idx - g * uQ;
+      const unsigned b = (B == 1) ? 0u : divN.div(g), lr = g - b * un;
       uint32_t x[4];
       philox4x32_10(q, (uint32_t)r_begin + lr, call, b, seed_lo, seed_hi, x);
       const float2 z0 = box_muller(x[0], x[1]), z1 = box_muller(x[2], x[3]);
@@ -136,7 +153,7 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p) {
 // coalesced (each row is T contiguous float2), accumulating the weighted sum per column.  The last
 // CTA of a controller to finish (atomic ticket) adds the per-CTA partials in fixed order, so results
 // are bitwise reproducible run to run.
-__global__ void __launch_bounds__(256) weight_reduce_kernel(const __grid_constant__ WeightParams p) {
+__global__ void __launch_bounds__(256, 8) weight_reduce_kernel(const __grid_constant__ WeightParams p) {
   extern __shared__ float sm[];
   float *w = sm;                               // [rows_per_blk]
   float2 *colsum = reinterpret_cast<float2 *>(sm + ((p.rows_per_blk + 3) & ~3));  // [nrl][T]
