@@ -9,8 +9,8 @@ One "step" = one complete computeControl pipeline (Philox noise -> fused rollout
 weighting -> Savitzky-Golay -> nominal trajectory) of BASELINE.json configs[1]: path_integral_nn,
 1920 rollouts x 100 timesteps on the synthetic ellipse costmap.  At N > 1 every rank runs one such
 controller (batched-MPC sharding: independent controllers, no communication) for `value`, and the
-1M-rollout configuration sharded over the ranks with one NCCL all-gather per step is reported under
-"sharded_large".  Prints ONE JSON line on rank 0.
+1M-rollout configuration sharded over the ranks is reported under "sharded_large", once with the 816-byte exchange
+fused into the weighting / finalize kernels over NVLink peer memory and once with one NCCL all-gather per step.  Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
