@@ -237,6 +237,16 @@ struct NeuralNetDyn {
   }
 };
 
+// x / c without the slow-path branch of the IEEE division sequence (FCHK + call), which serialises the 22 divisions of
+// the basis functions behind each other.  Markstein's refinement: with rc = RN(1 / c), q = RN(x rc), r = x - q c (exact,
+// one FMA), RN(q + r rc) is the correctly rounded quotient (outside overflow / underflow), i.e. the bits of x / c.
+__device__ __forceinline__ float div_refined(float x, float c, float rc) {
+  const float q = __fmul_rn(x, rc);
+  const float r = fmaf(-q, c, x);
+  return fmaf(r, rc, q);
+}
+#define MPPI_DIVC(x, c) div_refined((x), (c), 1.0f / (c))
+
 struct CarBasisDyn {
   static constexpr int R = 1;
   static constexpr int SMEM_FLOATS = 100;  // theta 4 x 25 row-major
@@ -244,36 +254,39 @@ struct CarBasisDyn {
   __device__ __forceinline__ static void deriv(const float *__restrict__ sw, float *, const float (&in)[6][1], float (&out)[4][1]) {
     const float roll = in[0][0], vx = in[1][0], vy = in[2][0], wz = in[3][0], steer = in[4][0], thr = in[5][0];
     const bool moving = vx >= 0.1f;  // (double)vx > .1  <=>  vx >= 0.1f because 0.1f > 0.1
-    const float ratio_y = __fdiv_rn(vy, vx);
+    // the three divisions by u_x share one reciprocal (MUFU.RCP + one Newton step: within 1 ulp, then Markstein's step)
+    const float r0 = rcp_approx(vx);
+    const float rvx = fmaf(fmaf(-vx, r0, 1.0f), r0, r0);
+    const float ratio_y = div_refined(vy, vx, rvx);
     // front: tan(atan(vy/vx + .45 wz/vx) - steer); rear: vy/vx - .35 wz/vx
-    const float front_arg = moving ? (ratio_y + 0.45f * wz / vx) : 0.0f;
+    const float front_arg = moving ? (ratio_y + div_refined(0.45f * wz, vx, rvx)) : 0.0f;
     const float tf = moving ? tanf(atanf(front_arg) - steer) : tanf(-steer);
-    const float rear = ratio_y - 0.35f * wz / vx;
+    const float rear = ratio_y - div_refined(0.35f * wz, vx, rvx);
     const float ss = sinf(steer);
     float phi[25];
     phi[0] = thr;
-    phi[1] = vx / 10.0f;
-    phi[2] = ss * tf / 1200.0f;
-    phi[3] = ss * tf * fabsf(tf) / 1440000.0f;
-    phi[4] = ss * (tf * tf * tf) / 1728000000.0f;
-    phi[5] = wz * vy / 25.0f;
-    phi[6] = wz / 10.0f;
-    phi[7] = vy / 10.0f;
+    phi[1] = MPPI_DIVC(vx, 10.0f);
+    phi[2] = MPPI_DIVC(ss * tf, 1200.0f);
+    phi[3] = MPPI_DIVC(ss * tf * fabsf(tf), 1440000.0f);
+    phi[4] = MPPI_DIVC(ss * (tf * tf * tf), 1728000000.0f);
+    phi[5] = MPPI_DIVC(wz * vy, 25.0f);
+    phi[6] = MPPI_DIVC(wz, 10.0f);
+    phi[7] = MPPI_DIVC(vy, 10.0f);
     phi[8] = ss;
-    phi[9] = moving ? ratio_y / 40.0f : 0.0f;
-    phi[10] = tf / 1400.0f;
-    phi[11] = tf * fabsf(tf) / 1960000.0f;
-    phi[12] = (tf * tf * tf) / 2744000000.0f;
-    phi[13] = moving ? rear / 40.0f : 0.0f;
-    phi[14] = moving ? rear * fabsf(rear) / 1600.0f : 0.0f;
-    phi[15] = moving ? (rear * rear * rear) / 64000.0f : 0.0f;
-    phi[16] = wz * vx / 50.0f;
+    phi[9] = moving ? MPPI_DIVC(ratio_y, 40.0f) : 0.0f;
+    phi[10] = MPPI_DIVC(tf, 1400.0f);
+    phi[11] = MPPI_DIVC(tf * fabsf(tf), 1960000.0f);
+    phi[12] = MPPI_DIVC(tf * tf * tf, 2744000000.0f);
+    phi[13] = moving ? MPPI_DIVC(rear, 40.0f) : 0.0f;
+    phi[14] = moving ? MPPI_DIVC(rear * fabsf(rear), 1600.0f) : 0.0f;
+    phi[15] = moving ? MPPI_DIVC(rear * rear * rear, 64000.0f) : 0.0f;
+    phi[16] = MPPI_DIVC(wz * vx, 50.0f);
     phi[17] = roll;
     phi[18] = roll * wz;
-    phi[19] = roll * vx / 3.0f;
-    phi[20] = roll * vx * wz / 5.0f;
-    phi[21] = vx * vx / 100.0f;
-    phi[22] = vx * vx * vx / 1000.0f;
+    phi[19] = MPPI_DIVC(roll * vx, 3.0f);
+    phi[20] = MPPI_DIVC(roll * vx * wz, 5.0f);
+    phi[21] = MPPI_DIVC(vx * vx, 100.0f);
+    phi[22] = MPPI_DIVC(vx * vx * vx, 1000.0f);
     phi[23] = thr * thr;
     phi[24] = thr * thr * thr;
 #pragma unroll
