@@ -444,6 +444,29 @@ def run_sharded_large(models, costmap, cp, state, U, world, rank, local_rank, ba
     ms = timed()
     sf = ctx.shard_floats()
     ctx.close()
+    # the latency end of the same protocol: the 1920-rollout controller sharded over the ranks (the rollout kernel is a
+    # dependent chain of 100 timesteps, so sharding cannot shorten it; what shows here is the cost of the exchange itself)
+    lo_s, n_s = rollout_shard(rank, world, N_ROLLOUTS)
+    small = {}
+    cs = make_context("nn", models, costmap, cp, N_ROLLOUTS, rollout_begin=lo_s, rollout_count=n_s, device=local_rank)
+    cs.comm_init(_fresh_id(dist, rank), rank, world)
+    cs.compute_control_sharded(state, U)
+
+    def timed_small(k=200):
+        cs.run_resident_sharded(20)
+        barrier()
+        cs.run_resident_sharded(1)
+        t = cs.run_resident_sharded(k)
+        barrier()
+        return max_over_ranks(t) / k
+    small["ms_per_step_nccl_allgather"] = timed_small()
+    hs = [None] * world
+    dist.all_gather_object(hs, cs.p2p_export(world))
+    cs.p2p_init(b"".join(hs), rank, world)
+    cs.compute_control_sharded(state, U)
+    small["ms_per_step"] = timed_small()
+    small["rollouts_per_gpu"] = n_s
+    cs.close()
     return {"rollouts": LARGE_ROLLOUTS, "rollouts_per_gpu": n, "steps": steps, "ms_per_step": ms / steps,
             "value": LARGE_ROLLOUTS * T_STEPS * steps / (ms * 1e-3), "unit": "rollout-steps/s", "scaling": "strong",
             "exchange": "peer-memory: the weighting kernel stores each rank's %d-float record into every GPU's mailbox over "
@@ -451,7 +474,14 @@ def run_sharded_large(models, costmap, cp, state, U, world, rank, local_rank, ba
             "ms_per_step_nccl_allgather": ms_nccl / steps,
             "value_nccl_allgather": LARGE_ROLLOUTS * T_STEPS * steps / (ms_nccl * 1e-3),
             "timing": "CUDA events on the context's stream, max over ranks", "normalizer": float(out_p2p["normalizer"]),
-            "normalizer_nccl": float(out["normalizer"])}
+            "normalizer_nccl": float(out["normalizer"]), "sharded_1920": small}
+
+
+def _fresh_id(dist, rank):
+    from autorally_b200.capi import MppiContext
+    ids = [MppiContext.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    return ids[0]
 
 
 if __name__ == "__main__":
