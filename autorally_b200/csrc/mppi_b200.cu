@@ -82,6 +82,9 @@ struct mppi_ctx {
   unsigned char *d_crash = nullptr;
   unsigned int *d_baseline = nullptr, *d_done = nullptr;
   float *d_block_partials = nullptr, *d_shard = nullptr;
+  // single GPU, one controller, few weighting CTAs: finalize_kernel adds the per-CTA partial records up itself and the
+  // weighting kernel skips its ticket / last-CTA pass; set around the launches of the plain (unsharded) pipeline only
+  bool direct_combine = false;
   double *d_inv_step = nullptr;
   int nblk = 1, rows_per_blk = 1;
   // noise
@@ -209,13 +212,15 @@ cudaError_t launch_weighting(mppi_ctx *c) {
   p.costs = c->d_costs; p.V = reinterpret_cast<const float2 *>(c->d_du); p.baseline = c->d_baseline;
   p.block_partials = c->d_block_partials; p.shard = c->d_shard; p.done_counter = c->d_done;
   p.n_local = c->n_local; p.T = c->T; p.nblk = c->nblk; p.rows_per_blk = c->rows_per_blk; p.shard_floats = c->shard_floats;
-  p.gamma = c->gamma;
+  p.gamma = c->gamma; p.partials_only = c->direct_combine ? 1 : 0;
   p.G = c->p2p_send ? c->p2p_size : 1; p.rank = c->p2p_rank; p.B = c->B; p.seq = c->p2p_seq;
   p.peer_mailbox = c->d_peer_mailbox; p.peer_flags = c->d_peer_flags;
   const int nrl = std::max(1, 256 / c->T);
   const size_t smem = (size_t)round_up(c->rows_per_blk, 4) * 4 + (size_t)nrl * c->T * 8;
   c->launches++;
-  return launch_pdl(c, weight_reduce_kernel, dim3(c->nblk, c->B), 256, smem, c->pdl, p);
+  // few CTAs (latency configurations): more loads in flight per thread; the filled GPU needs 8 CTAs per SM (32 registers)
+  if ((long long)c->nblk * c->B <= 148LL * 2) return launch_pdl(c, weight_reduce_kernel<16, 2>, dim3(c->nblk, c->B), 256, smem, c->pdl, p);
+  return launch_pdl(c, weight_reduce_kernel<8, 8>, dim3(c->nblk, c->B), 256, smem, c->pdl, p);
 }
 
 size_t finalize_smem(const mppi_ctx *c) {
@@ -225,6 +230,7 @@ size_t finalize_smem(const mppi_ctx *c) {
 
 cudaError_t launch_finalize(mppi_ctx *c, const float *gathered, int G, int last_iter, int feed_back, bool push_outbox = false) {
   FinalizeParams p{};
+  if (c->direct_combine && gathered == c->d_shard) { gathered = c->d_block_partials; p.combine_partials = c->nblk; }
   p.gathered = gathered; p.inbox = c->d_inbox; p.outbox = push_outbox ? c->h_outbox_dev : c->d_outbox; p.theta_t = c->d_theta_t;
   p.net_structure = c->d_net_structure;
   p.num_layers = c->cfg.dynamics == MPPI_DYNAMICS_BF ? 0 : (int)c->net_structure.size();
@@ -239,7 +245,7 @@ cudaError_t launch_finalize(mppi_ctx *c, const float *gathered, int G, int last_
   c->launches++;
   // after an NCCL exchange (gathered != own shard) the predecessor is not one of our kernels: plain launch
   // many batched controllers: small CTAs, so that more of the single-warp nominal trajectories are resident per SM
-  return launch_pdl(c, finalize_kernel, dim3(c->B), c->B >= 64 ? 64 : 256, finalize_smem(c), c->pdl && gathered == c->d_shard, p);
+  return launch_pdl(c, finalize_kernel, dim3(c->B), c->B >= 64 ? 64 : 256, finalize_smem(c), c->pdl && (gathered == c->d_shard || p.combine_partials > 0), p);
 }
 
 int check_ready(const mppi_ctx *c) {
@@ -343,6 +349,9 @@ int mppi_create(const mppi_config *cfg, mppi_ctx **out) {
   {
     long long want = std::max(1LL, (148LL * 8) / c->B);
     long long nblk = std::min<long long>(want, (c->n_local + 31) / 32);
+    // one controller of up to 4096 rollouts: at most 32 CTAs, so that finalize_kernel can add the partial records up itself
+    // in two batches of 16 loads (wider batches cost finalize_kernel registers its nominal-trajectory warp needs: measured)
+    if (c->B == 1 && nblk > 32 && nblk <= 128) nblk = 32;
     c->rows_per_blk = (int)((c->n_local + nblk - 1) / nblk);
     c->nblk = (c->n_local + c->rows_per_blk - 1) / c->rows_per_blk;
   }
@@ -575,7 +584,16 @@ int mppi_sample_noise(mppi_ctx *c, float *eps_out) {
   return MPPI_OK;
 }
 
+// Scope guard: the plain single-GPU pipeline of one controller with at most 32 weighting CTAs lets finalize_kernel add
+// up the per-CTA partial records (see FinalizeParams::combine_partials); every other path keeps the shard record.
+struct DirectCombineScope {
+  mppi_ctx *c;
+  explicit DirectCombineScope(mppi_ctx *ctx) : c(ctx) { c->direct_combine = (c->B == 1 && c->nblk <= 32 && c->T <= 256); }
+  ~DirectCombineScope() { c->direct_combine = false; }
+};
+
 static int enqueue_compute(mppi_ctx *c) {
+  DirectCombineScope direct(c);
   // Zero-copy for the small per-call payloads (state / U / history in, results out): the sampler kernel pulls the inbox
   // from mapped pinned memory and finalize_kernel writes the outbox into it, which removes the two copy nodes of the
   // graph (the same bytes still cross PCIe).  Injected-noise runs and large batches use explicit copies.
@@ -971,6 +989,7 @@ int mppi_run_resident(mppi_ctx *c, int steps, int flush_l2, float *elapsed_ms, f
   }
   if (flush_l2 && !c->d_flush) CK(cudaMalloc(&c->d_flush, kFlushBytes));
   c->launches = 0;
+  DirectCombineScope direct(c);
   CK(cudaEventRecord(c->ev0, c->stream));
   for (int s = 0; s < steps; s++) {
     if (flush_l2) CK(cudaMemsetAsync(c->d_flush, s & 0xff, kFlushBytes, c->stream));

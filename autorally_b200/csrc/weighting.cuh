@@ -123,6 +123,7 @@ struct WeightParams {
   unsigned int *done_counter;    // [B]
   int n_local, T, nblk, rows_per_blk, shard_floats;
   float gamma;
+  int partials_only;  // 1: stop after the per-CTA partial records; finalize_kernel adds them up itself (combine_partials)
   // Peer-memory exchange (multi-GPU, mppi_p2p_init): the CTA that finishes a controller's shard record also stores it
   // into the mailbox of every GPU -- over NVLink for the peers -- and then raises that GPU's flag for (rank, controller)
   // to `seq`.  peer_mailbox[g] = GPU g's mailbox [2][G][B][shard_floats], peer_flags[g] = its flags [2][G][B].
@@ -147,13 +148,32 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p) {
   return v;
 }
 
-// grid (nblk, B), block 256.  Each CTA owns rows_per_blk rollouts of one controller: it turns their
-// costs into weights in shared memory (exp-normalisation against the baseline the rollout kernel
-// left behind), block-reduces Z and Q with warp shuffles, and streams the rows' sampled controls once,
-// coalesced (each row is T contiguous float2), accumulating the weighted sum per column.  The last
-// CTA of a controller to finish (atomic ticket) adds the per-CTA partials in fixed order, so results
-// are bitwise reproducible run to run.
-__global__ void __launch_bounds__(256, 8) weight_reduce_kernel(const __grid_constant__ WeightParams p) {
+// Entry k of the per-CTA partial records summed over the CTAs in a fixed order (bitwise reproducible run to run), with 16
+// independent L2 loads in flight per thread (the partials were just written by other SMs).
+__device__ __forceinline__ float sum_partials_fixed_order(const float *parts, int nblk, int shard_floats, int k) {
+  float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+  int j = 0;
+  for (; j + 15 < nblk; j += 16) {
+    float v[16];
+#pragma unroll
+    for (int m = 0; m < 16; m++) v[m] = __ldcg(parts + (size_t)(j + m) * shard_floats + k);
+#pragma unroll
+    for (int m = 0; m < 16; m += 4) { a0 += v[m]; a1 += v[m + 1]; a2 += v[m + 2]; a3 += v[m + 3]; }
+  }
+  for (; j + 3 < nblk; j += 4) {
+    a0 += __ldcg(parts + (size_t)j * shard_floats + k);
+    a1 += __ldcg(parts + (size_t)(j + 1) * shard_floats + k);
+    a2 += __ldcg(parts + (size_t)(j + 2) * shard_floats + k);
+    a3 += __ldcg(parts + (size_t)(j + 3) * shard_floats + k);
+  }
+  for (; j < nblk; j++) a0 += __ldcg(parts + (size_t)j * shard_floats + k);
+  return (a0 + a1) + (a2 + a3);
+}
+
+// ROWS_IN_FLIGHT independent row loads per thread: 8 keeps the kernel at 32 registers (8 CTAs per SM, one wave of 148 x 8
+// CTAs for the filled GPU); the small grids of the latency configurations use 16 (one L2 round trip per 32-row CTA).
+template <int ROWS_IN_FLIGHT, int MIN_CTAS>
+__global__ void __launch_bounds__(256, MIN_CTAS) weight_reduce_kernel(const __grid_constant__ WeightParams p) {
   extern __shared__ float sm[];
   float *w = sm;                               // [rows_per_blk]
   float2 *colsum = reinterpret_cast<float2 *>(sm + ((p.rows_per_blk + 3) & ~3));  // [nrl][T]
@@ -190,16 +210,20 @@ __global__ void __launch_bounds__(256, 8) weight_reduce_kernel(const __grid_cons
     float2 acc = make_float2(0.0f, 0.0f);
     if (rl < nrl && c < T) {
       int i = rl;
-      for (; i + 7 * nrl < nrows; i += 8 * nrl) {  // 8 independent row loads in flight, accumulated in row order
-        float2 v[8];
+      for (; i + (ROWS_IN_FLIGHT - 1) * nrl < nrows; i += ROWS_IN_FLIGHT * nrl) {  // independent row loads in flight, accumulated in row order
+        float2 v[ROWS_IN_FLIGHT];
 #pragma unroll
-        for (int m = 0; m < 8; m++) v[m] = V[(size_t)(i + m * nrl) * T + c];
+        for (int m = 0; m < ROWS_IN_FLIGHT; m++) v[m] = V[(size_t)(i + m * nrl) * T + c];
 #pragma unroll
-        for (int m = 0; m < 8; m++) { acc.x = fmaf(w[i + m * nrl], v[m].x, acc.x); acc.y = fmaf(w[i + m * nrl], v[m].y, acc.y); }
+        for (int m = 0; m < ROWS_IN_FLIGHT; m++) { acc.x = fmaf(w[i + m * nrl], v[m].x, acc.x); acc.y = fmaf(w[i + m * nrl], v[m].y, acc.y); }
       }
-      for (; i < nrows; i += nrl) {
-        const float2 v = V[(size_t)i * T + c];
-        acc.x = fmaf(w[i], v.x, acc.x); acc.y = fmaf(w[i], v.y, acc.y);
+      if (i < nrows) {  // the remaining rows as one predicated batch (a serial tail would be one L2 round trip per row)
+        float2 v[ROWS_IN_FLIGHT];
+#pragma unroll
+        for (int m = 0; m < ROWS_IN_FLIGHT; m++) v[m] = (i + m * nrl < nrows) ? V[(size_t)(i + m * nrl) * T + c] : make_float2(0.0f, 0.0f);
+#pragma unroll
+        for (int m = 0; m < ROWS_IN_FLIGHT; m++)
+          if (i + m * nrl < nrows) { acc.x = fmaf(w[i + m * nrl], v[m].x, acc.x); acc.y = fmaf(w[i + m * nrl], v[m].y, acc.y); }
       }
       colsum[rl * T + c] = acc;
     }
@@ -219,6 +243,7 @@ __global__ void __launch_bounds__(256, 8) weight_reduce_kernel(const __grid_cons
     for (int i = 0; i < 8; i++) { zz += red[0][i]; qq += red[1][i]; }
     out[0] = base; out[1] = zz; out[2] = qq; out[3] = 0.0f;
   }
+  if (p.partials_only) return;
   // ---- last CTA of this controller combines the per-CTA partials in fixed order ----
   __threadfence();
   __syncthreads();
@@ -235,25 +260,7 @@ __global__ void __launch_bounds__(256, 8) weight_reduce_kernel(const __grid_cons
   for (int k = tid; k < p.shard_floats; k += 256) {
     if (k == 0) { shard[0] = base; continue; }
     if (k == 3 || k >= SHARD_HDR + 2 * T) { shard[k] = 0.0f; continue; }
-    // 16 independent L2 loads in flight per thread (the partials were just written by other SMs); the summation
-    // order is fixed, so the result is bitwise reproducible run to run
-    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-    int j = 0;
-    for (; j + 15 < p.nblk; j += 16) {
-      float v[16];
-#pragma unroll
-      for (int m = 0; m < 16; m++) v[m] = __ldcg(parts + (size_t)(j + m) * p.shard_floats + k);
-#pragma unroll
-      for (int m = 0; m < 16; m += 4) { a0 += v[m]; a1 += v[m + 1]; a2 += v[m + 2]; a3 += v[m + 3]; }
-    }
-    for (; j + 3 < p.nblk; j += 4) {
-      a0 += __ldcg(parts + (size_t)j * p.shard_floats + k);
-      a1 += __ldcg(parts + (size_t)(j + 1) * p.shard_floats + k);
-      a2 += __ldcg(parts + (size_t)(j + 2) * p.shard_floats + k);
-      a3 += __ldcg(parts + (size_t)(j + 3) * p.shard_floats + k);
-    }
-    for (; j < p.nblk; j++) a0 += __ldcg(parts + (size_t)j * p.shard_floats + k);
-    shard[k] = (a0 + a1) + (a2 + a3);
+    shard[k] = sum_partials_fixed_order(parts, p.nblk, p.shard_floats, k);
   }
   if (p.G > 1) {
     // fused exchange: this CTA's record goes straight into every GPU's mailbox (peer stores over NVLink), then the flags
@@ -273,6 +280,10 @@ __global__ void __launch_bounds__(256, 8) weight_reduce_kernel(const __grid_cons
 // ------------------------------------------------------------------------------ finalize ----
 struct FinalizeParams {
   const float *gathered;  // [G][B][shard_floats]
+  // combine_partials > 0: `gathered` is the weighting kernel's per-CTA partial records [combine_partials][shard_floats] of
+  // ONE controller (B == 1, G == 1); this kernel adds them up in the fixed order of sum_partials_fixed_order, which
+  // spares the weighting kernel its fence / atomic-ticket / last-CTA pass (three dependent L2 round trips)
+  int combine_partials;
   float *inbox;           // [B][inbox_stride]  (U is rewritten for the next iteration / resident step)
   float *outbox;          // [B][outbox_stride]: result[4] | U_smoothed[2T] | U_new[2T] | state_sol[7T] | ctrl_sol[2T]
   const float *theta_t;   // NN: transposed packed weights; BF: theta 4x25
@@ -364,6 +375,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ F
   float *Usm = Unew + 2 * T;         // [2T]
   float *act = Usm + 2 * T;          // [2][FIN_MAX_WIDTH]
   float *sw = act + 2 * FIN_MAX_WIDTH;  // staged parameters
+  __shared__ float rec_sm[4 + 2 * 256 + 4];  // the combined record (combine_partials; T <= 256)
   __shared__ float scale[64];
   __shared__ float hdr[4];
   float *inbox = p.inbox + (size_t)b * p.inbox_stride;
@@ -385,12 +397,25 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ F
     __syncthreads();
   }
 
+  const float *gathered = p.gathered;
+  if (p.combine_partials > 0) {
+    for (int k = tid; k < p.shard_floats; k += nthr) {
+      float v;
+      if (k == 0) v = __ldcg(p.gathered);                                  // every CTA used the same global baseline
+      else if (k == 3 || k >= SHARD_HDR + 2 * T) v = 0.0f;
+      else v = sum_partials_fixed_order(p.gathered, p.combine_partials, p.shard_floats, k);
+      rec_sm[k] = v;
+    }
+    __syncthreads();
+    gathered = rec_sm;
+  }
+
   if (tid == 0) {
-    float base = p.gathered[((size_t)0 * p.B + b) * p.shard_floats];
-    for (int g = 1; g < p.G; g++) base = fminf(base, p.gathered[((size_t)g * p.B + b) * p.shard_floats]);
+    float base = gathered[((size_t)0 * p.B + b) * p.shard_floats];
+    for (int g = 1; g < p.G; g++) base = fminf(base, gathered[((size_t)g * p.B + b) * p.shard_floats]);
     float Z = 0.0f, Q = 0.0f;
     for (int g = 0; g < p.G; g++) {
-      const float *rec = p.gathered + ((size_t)g * p.B + b) * p.shard_floats;
+      const float *rec = gathered + ((size_t)g * p.B + b) * p.shard_floats;
       const float sg = (p.G == 1) ? 1.0f : expf(-p.gamma * (rec[0] - base));
       scale[g] = sg;
       Z = fmaf(sg, rec[1], Z);
@@ -402,7 +427,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ F
   const float Z = hdr[1];
   for (int k = tid; k < 2 * T; k += nthr) {
     float wsum = 0.0f;
-    for (int g = 0; g < p.G; g++) wsum = fmaf(scale[g], p.gathered[((size_t)g * p.B + b) * p.shard_floats + SHARD_HDR + k], wsum);
+    for (int g = 0; g < p.G; g++) wsum = fmaf(scale[g], gathered[((size_t)g * p.B + b) * p.shard_floats + SHARD_HDR + k], wsum);
     Unew[k] = wsum / Z;
   }
   if (tid < 4) outbox[tid] = hdr[tid];
