@@ -136,7 +136,12 @@ int resolve_variant(const mppi_ctx *c) {
   int v = c->cfg.rollout_variant;
   const long long total = (long long)c->B * c->n_local;
   if (c->cfg.dynamics == MPPI_DYNAMICS_BF) return MPPI_ROLLOUT_THREAD1;
-  if (c->net_kind == 64) return MPPI_ROLLOUT_THREAD1;
+  if (c->net_kind == 64) {
+    // 6-64-64-64-64-4: the tensor-core kernel at every size (1920 x 100: 5.4 ms -> see profiles/exp_tc64_r01.txt); the
+    // one-rollout-per-thread FP32 kernel stays selectable and is the fallback for out-of-range biases
+    if (v != MPPI_ROLLOUT_AUTO && v != MPPI_ROLLOUT_TENSOR) return MPPI_ROLLOUT_THREAD1;
+    return (c->theta_t.size() >= 13188 && tc_biases_in_range(c->theta_t.data(), 64, 4)) ? MPPI_ROLLOUT_TENSOR : MPPI_ROLLOUT_THREAD1;
+  }
   if (v == MPPI_ROLLOUT_AUTO) {
     // Measured on B200 (profiles/exp_tc_r01.txt, rollout kernel only): one rollout per half-warp wins up to 16384 rollouts
     // (233 us vs 280 us for the tensor-core kernel), loses from 32768 (434 us vs 335 us); the FFMA2 kernel (THREAD2) is
@@ -144,15 +149,9 @@ int resolve_variant(const mppi_ctx *c) {
     if (total <= 24576) v = MPPI_ROLLOUT_HALF16;
     else v = MPPI_ROLLOUT_TENSOR;
   }
-  if (v == MPPI_ROLLOUT_TENSOR) {
-    // the tensor-core kernel folds the hidden-layer biases into its exponentials as e^(2 b1) and e^(2 (b2 + rowsum W2))
-    // (rollout_tc.cu): beyond +-40 these would leave the FP32 range, so such a network runs on the FFMA2 kernel instead
-    for (int j = 0; j < 32 && c->theta_t.size() >= 1412; j++) {
-      double s2 = c->theta_t[1248 + j];
-      for (int k = 0; k < 32; k++) s2 += (double)c->theta_t[224 + k * 32 + j];
-      if (!(std::fabs(c->theta_t[192 + j]) < 40.0f) || !(std::fabs(s2) < 40.0)) v = MPPI_ROLLOUT_THREAD2;
-    }
-  }
+  // the tensor-core kernel folds the hidden-layer biases into its exponentials as e^(2 b1) and e^(2 (b2 + rowsum W2))
+  // (rollout_tc.cu): beyond +-40 these would leave the FP32 range, so such a network runs on the FFMA2 kernel instead
+  if (v == MPPI_ROLLOUT_TENSOR && !(c->theta_t.size() >= 1412 && tc_biases_in_range(c->theta_t.data(), 32, 2))) v = MPPI_ROLLOUT_THREAD2;
   if (v == MPPI_ROLLOUT_CONST1) v = MPPI_ROLLOUT_THREAD2;  // constant-bank weights measured no faster (profiles/microbench_r01.txt)
   return v;
 }
@@ -182,7 +181,8 @@ cudaError_t launch_rollout(mppi_ctx *c) {
   const bool small = total <= 148LL * 4 * 32 * 4;
   c->launches++;
   if (c->cfg.dynamics == MPPI_DYNAMICS_BF) return launch_rollout_bf(p, c->stream, small);
-  if (c->net_kind == 64) return launch_rollout_nn64_r1(p, c->stream, small);
+  if (c->net_kind == 64)
+    return c->variant == MPPI_ROLLOUT_TENSOR ? launch_rollout_nn64_tc(p, c->stream, c->theta_t.data()) : launch_rollout_nn64_r1(p, c->stream, small);
   switch (c->variant) {
     case MPPI_ROLLOUT_THREAD2: return launch_rollout_nn32_r2(p, c->stream, small);
     case MPPI_ROLLOUT_SPLIT8: return launch_rollout_nn32_split8(p, c->stream);

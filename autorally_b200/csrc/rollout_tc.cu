@@ -46,21 +46,38 @@ namespace tc {
 #endif
 
 constexpr int TILE = 128;         // rollouts per CTA = TMEM lanes
-constexpr int TMEM_COLS = 64;     // allocation (power of two); 8 CTAs per SM
-constexpr int COL_D = 0;          // accumulator, 32 columns
-constexpr int COL_A = 32;         // activations: [hi(0..15) | lo(0..15) | hi(16..31) | lo(16..31)], 8 columns each
 constexpr float TANH_SCALE = 2.88539008177792681472f;  // 2 log2(e)
 
-// shared-memory B matrices (FP16, canonical K-major no-swizzle: 8 rows x 16 bytes core matrices)
-constexpr int OFF_B1A = 0;               // N=32 K=16: W1_hi twice (against [a_hi | a_lo])
-constexpr int OFF_B1B = OFF_B1A + 1024;  // N=32 K=16: W1_lo, 0
-constexpr int OFF_B2H = OFF_B1B + 1024;  // N=32 K=32
-constexpr int OFF_B2L = OFF_B2H + 2048;
-constexpr int OFF_B3H = OFF_B2L + 2048;  // N=16 K=32 (4 real output rows)
-constexpr int OFF_B3L = OFF_B3H + 1024;
-constexpr int B_BYTES = OFF_B3L + 1024;
-// keeps residency at 8 CTAs per SM (8 x 64 TMEM columns): a ninth CTA would only spin in tcgen05.alloc
-constexpr int SMEM_PAD_BYTES = 24 * 1024;
+// Geometry of one instantiation: 6 -> HID x NHID (tanh) -> 4.  NeuralNetModel<7,2,3,6,32,32,4> is <32, 2>, the
+// wider_deeper network 6-64-64-64-64-4 the fork ships (SRC/params/models/wider_deeper_network_08_20_2020.npz) <64, 4>.
+template <int HID, int NHID>
+struct Geo {
+  static_assert(HID == 32 || HID == 64, "hidden width 32 or 64");
+  static_assert(NHID >= 2, "at least two hidden layers");
+  static constexpr int NCH = HID / 16;                    // K = 16 chunks per hidden layer = 16-column epilogue chunks
+  static constexpr int COL_D = 0;                         // accumulator, HID columns
+  static constexpr int COL_A = HID;                       // activations: per chunk [hi(16 neurons) | lo(16 neurons)], 8 + 8 columns
+  static constexpr int TMEM_COLS = 2 * HID;               // power of two: 64 (8 CTAs per SM) or 128
+  // shared-memory B matrices (FP16, canonical K-major no-swizzle: 8 rows x 16 bytes core matrices)
+  static constexpr int SZ_B1 = HID * 16 * 2;              // N = HID, K = 16
+  static constexpr int SZ_BH = HID * HID * 2;             // N = HID, K = HID
+  static constexpr int SZ_BL = 16 * HID * 2;              // N = 16 (4 real output rows), K = HID
+  static constexpr int OFF_B1A = 0;                       // W1_hi twice (against [a_hi | a_lo])
+  static constexpr int OFF_B1B = SZ_B1;                   // W1_lo, 0
+  static constexpr int OFF_BH = 2 * SZ_B1;                // hidden layer h = 1 .. NHID-1: hi at OFF_BH + (h-1) 2 SZ_BH, lo after it
+  static constexpr int OFF_BL = OFF_BH + (NHID - 1) * 2 * SZ_BH;  // last layer: hi, lo
+  static constexpr int B_BYTES = OFF_BL + 2 * SZ_BL;
+  // HID = 32: the pad keeps residency at 8 CTAs per SM (8 x 64 TMEM columns): a ninth CTA would only spin in
+  // tcgen05.alloc.  HID = 64: 56 KB of weights, 3 CTAs per SM (4 x 128 columns would fit, shared memory does not).
+  static constexpr int SMEM_BYTES = B_BYTES < 24 * 1024 ? 24 * 1024 : B_BYTES;
+  static constexpr int MIN_CTAS = HID == 32 ? 8 : 3;
+  // packed transposed parameters: per layer Wt[k][j] then b[j]
+  static constexpr int TH_W1 = 0, TH_B1 = 6 * HID;
+  __host__ __device__ static constexpr int th_w(int h) { return 7 * HID + (h - 1) * (HID * HID + HID); }       // hidden layer h >= 1
+  __host__ __device__ static constexpr int th_b(int h) { return th_w(h) + HID * HID; }
+  static constexpr int TH_WL = 7 * HID + (NHID - 1) * (HID * HID + HID), TH_BL = TH_WL + HID * 4;
+  static constexpr int NPARAMS = TH_BL + 4;
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -150,9 +167,12 @@ __device__ __forceinline__ void split2(float x0, float x1, uint32_t &hi, uint32_
   lo = *reinterpret_cast<const uint32_t *>(&l);
 }
 
-// Epilogue constants, in the kernel parameter block (constant bank): e^(2 b1), e^(2 (b2 + rowsum W2)), b3 + rowsum W3.
+// Epilogue constants, in the kernel parameter block (constant bank): e^(2 b) of the first hidden layer,
+// e^(2 (b + rowsum W)) of the following ones, b + rowsum W of the output layer.
+template <int HID, int NHID>
 struct TcEpilogue {
-  float eb1[32], eb2[32], b3[4];
+  float eb[NHID][HID];
+  float b_last[4];
 };
 
 // r = 1 / (2^x eb + 1) for four neurons (tanh(.) = 1 - 2r); x already scaled by 2 log2(e), eb = 2^(scaled bias).
@@ -203,30 +223,37 @@ __device__ __forceinline__ void put_split(unsigned char *hi_base, unsigned char 
   if (lo_base) *reinterpret_cast<__half *>(lo_base + b_off(N, n, k)) = l;
 }
 
-__global__ void __launch_bounds__(TILE, 8) rollout_tc_kernel(const __grid_constant__ RolloutParams p, const __grid_constant__ TcEpilogue ep) {
+template <int HID, int NHID>
+__global__ void __launch_bounds__(TILE, Geo<HID, NHID>::MIN_CTAS)
+rollout_tc_kernel(const __grid_constant__ RolloutParams p, const __grid_constant__ TcEpilogue<HID, NHID> ep) {
+  using G = Geo<HID, NHID>;
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) unsigned long long mma_bar;
   __shared__ uint32_t tmem_base_slot;
   const int tid = threadIdx.x, warp = tid >> 5;
 
   // ---- prologue: weights -> FP16 hi / lo B matrices in shared memory (theta_t: per layer Wt[k][j], then b[j]) ----
-  for (int i = tid; i < B_BYTES / 16; i += TILE) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < G::B_BYTES / 16; i += TILE) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
   {
     const float *th = p.theta_t;
-    for (int i = tid; i < 6 * 32; i += TILE) {  // layer 1 weights, scaled
-      const int k = i >> 5, n = i & 31;
-      const float w = __fmul_rn(th[i], TANH_SCALE);
-      put_split(smem + OFF_B1A, smem + OFF_B1B, 32, n, k, w);
-      put_split(smem + OFF_B1A, nullptr, 32, n, 8 + k, w);
+    for (int i = tid; i < 6 * HID; i += TILE) {  // layer 1 weights, scaled
+      const int k = i / HID, n = i - k * HID;
+      const float w = __fmul_rn(th[G::TH_W1 + i], TANH_SCALE);
+      put_split(smem + G::OFF_B1A, smem + G::OFF_B1B, HID, n, k, w);
+      put_split(smem + G::OFF_B1A, nullptr, HID, n, 8 + k, w);
     }
-    for (int i = tid; i < 32 * 32; i += TILE) {  // layer 2 acts on r1: -2 W2 (and the tanh scale)
-      const int k = i >> 5, n = i & 31;
-      put_split(smem + OFF_B2H, smem + OFF_B2L, 32, n, k, __fmul_rn(th[224 + i], -2.0f * TANH_SCALE));
+#pragma unroll
+    for (int h = 1; h < NHID; h++) {  // hidden layer h acts on r of layer h - 1: -2 W (and the tanh scale)
+      unsigned char *hi = smem + G::OFF_BH + (h - 1) * 2 * G::SZ_BH;
+      for (int i = tid; i < HID * HID; i += TILE) {
+        const int k = i / HID, n = i - k * HID;
+        put_split(hi, hi + G::SZ_BH, HID, n, k, __fmul_rn(th[G::th_w(h) + i], -2.0f * TANH_SCALE));
+      }
     }
-    for (int i = tid; i < 32 * 4; i += TILE) {  // layer 3 acts on r2: -2 W3 (linear output, no tanh scale)
+    for (int i = tid; i < HID * 4; i += TILE) {  // output layer acts on r of the last hidden layer: -2 W (linear, no tanh scale)
       const int k = i >> 2, n = i & 3;
-      put_split(smem + OFF_B3H, smem + OFF_B3L, 16, n, k, -2.0f * th[1280 + i]);
+      put_split(smem + G::OFF_BL, smem + G::OFF_BL + G::SZ_BL, 16, n, k, -2.0f * th[G::TH_WL + i]);
     }
   }
   const uint32_t bar = smem_u32(&mma_bar);
@@ -235,7 +262,7 @@ __global__ void __launch_bounds__(TILE, 8) rollout_tc_kernel(const __grid_consta
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(G::TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy weight stores -> visible to the tensor core
@@ -246,7 +273,7 @@ __global__ void __launch_bounds__(TILE, 8) rollout_tc_kernel(const __grid_consta
   const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);  // this warp's 32 TMEM lanes
 
   const uint32_t sb = (smem_u32(smem) & 0x3FFFFu) >> 4;
-  constexpr uint32_t ID32 = idesc(128, 32), ID16 = idesc(128, 16);
+  constexpr uint32_t IDH = idesc(128, HID), ID16 = idesc(128, 16);
 
   // ---- rollout bookkeeping (rollout.cuh, R = 1) ----
   const long long total = (long long)p.B * p.n_local;
@@ -305,7 +332,7 @@ __global__ void __launch_bounds__(TILE, 8) rollout_tc_kernel(const __grid_consta
       a[2] = ua_hi; a[6] = ua_lo;
       a[3] = 0u;
       a[7] = 0u;
-      tmem_st8(lane_base + COL_A, a);
+      tmem_st8(lane_base + G::COL_A, a);
     }
     wait_st();
     fence_before();
@@ -313,8 +340,8 @@ __global__ void __launch_bounds__(TILE, 8) rollout_tc_kernel(const __grid_consta
     if (warp == 0 && TC_EXP != 3 && TC_EXP != 4) {
       if (tid == 0) {
         fence_after();
-        mma_ts(tmem + COL_D, tmem + COL_A, chunk_desc(sb, OFF_B1A, 32, 0), ID32, 0u);
-        mma_ts(tmem + COL_D, tmem + COL_A, chunk_desc(sb, OFF_B1B, 32, 0), ID32, 1u);
+        mma_ts(tmem + G::COL_D, tmem + G::COL_A, chunk_desc(sb, G::OFF_B1A, HID, 0), IDH, 0u);
+        mma_ts(tmem + G::COL_D, tmem + G::COL_A, chunk_desc(sb, G::OFF_B1B, HID, 0), IDH, 1u);
         mma_commit(bar);
       }
       __syncwarp();
@@ -333,20 +360,17 @@ __global__ void __launch_bounds__(TILE, 8) rollout_tc_kernel(const __grid_consta
     phase ^= 1u;
     fence_after();
 
-    // ---- layers 2 and 3: tanh epilogue -> hi / lo activations back into TMEM -> 6 MMAs each ----
+    // ---- following layers: tanh epilogue -> hi / lo activations back into TMEM -> 3 MMAs per K = 16 chunk ----
 #pragma unroll
-    for (int layer = 0; layer < 2; layer++) {
-      {
+    for (int layer = 1; layer <= NHID; layer++) {  // layer = index of the layer whose MMAs are issued here (NHID = output layer)
+#pragma unroll
+      for (int c = 0; c < G::NCH; c++) {
         float v[16];
         uint32_t h[16];
-        tmem_ld16(lane_base + COL_D, v);
+        tmem_ld16(lane_base + G::COL_D + 16 * c, v);
         wait_ld();
-        activate16(v, layer == 0 ? ep.eb1 : ep.eb2, h);
-        tmem_st16(lane_base + COL_A, h);
-        tmem_ld16(lane_base + COL_D + 16, v);
-        wait_ld();
-        activate16(v, (layer == 0 ? ep.eb1 : ep.eb2) + 16, h);
-        tmem_st16(lane_base + COL_A + 16, h);
+        activate16(v, &ep.eb[layer - 1][16 * c], h);
+        tmem_st16(lane_base + G::COL_A + 16 * c, h);
       }
       wait_st();
       fence_before();
@@ -354,22 +378,23 @@ __global__ void __launch_bounds__(TILE, 8) rollout_tc_kernel(const __grid_consta
       if (warp == 0 && TC_EXP != 3 && TC_EXP != 4) {
         if (tid == 0) {
           fence_after();
-          const int N = layer == 0 ? 32 : 16;
-          const uint32_t id = layer == 0 ? ID32 : ID16;
-          const int bh = layer == 0 ? OFF_B2H : OFF_B3H, bl = layer == 0 ? OFF_B2L : OFF_B3L;
-          mma_ts(tmem + COL_D, tmem + COL_A + 8, chunk_desc(sb, bh, N, 0), id, 0u);       // lo(0..15)  x W_hi
-          mma_ts(tmem + COL_D, tmem + COL_A + 24, chunk_desc(sb, bh, N, 1), id, 1u);      // lo(16..31) x W_hi
-          mma_ts(tmem + COL_D, tmem + COL_A + 0, chunk_desc(sb, bl, N, 0), id, 1u);       // hi(0..15)  x W_lo
-          mma_ts(tmem + COL_D, tmem + COL_A + 16, chunk_desc(sb, bl, N, 1), id, 1u);      // hi(16..31) x W_lo
-          mma_ts(tmem + COL_D, tmem + COL_A + 0, chunk_desc(sb, bh, N, 0), id, 1u);       // hi x W_hi
-          mma_ts(tmem + COL_D, tmem + COL_A + 16, chunk_desc(sb, bh, N, 1), id, 1u);
+          const bool last = (layer == NHID);
+          const int N = last ? 16 : HID;
+          const uint32_t id = last ? ID16 : IDH;
+          const int bh = last ? G::OFF_BL : G::OFF_BH + (layer - 1) * 2 * G::SZ_BH, bl = bh + (last ? G::SZ_BL : G::SZ_BH);
+#pragma unroll
+          for (int c = 0; c < G::NCH; c++) mma_ts(tmem + G::COL_D, tmem + G::COL_A + 16 * c + 8, chunk_desc(sb, bh, N, c), id, c > 0 ? 1u : 0u);  // lo x W_hi
+#pragma unroll
+          for (int c = 0; c < G::NCH; c++) mma_ts(tmem + G::COL_D, tmem + G::COL_A + 16 * c, chunk_desc(sb, bl, N, c), id, 1u);                  // hi x W_lo
+#pragma unroll
+          for (int c = 0; c < G::NCH; c++) mma_ts(tmem + G::COL_D, tmem + G::COL_A + 16 * c, chunk_desc(sb, bh, N, c), id, 1u);                  // hi x W_hi
           mma_commit(bar);
         }
         __syncwarp();
       }
-      if (layer == 1) break;
+      if (layer == NHID) break;
       // second wait: the stabilizing cost (atan of the slip angle), the NaN / 1e12 clamp and the running mean (:162-165)
-      if (i > 0 && TC_EXP != 1) {
+      if (layer == 1 && i > 0 && TC_EXP != 1) {
         float c = __fadd_rn(cost_acc, cost_stab_part(p.cp, s[4], s[5]));
         if (c > 1e12f || isnan(c)) c = 1e12f;
         running = (float)((double)running + (double)__fsub_rn(c, running) * p.inv_step[i]);
@@ -398,10 +423,10 @@ __global__ void __launch_bounds__(TILE, 8) rollout_tc_kernel(const __grid_consta
     phase ^= 1u;
     fence_after();
     float o[4];
-    tmem_ld4(lane_base + COL_D, o);
+    tmem_ld4(lane_base + G::COL_D, o);
     wait_ld();
 #pragma unroll
-    for (int k = 0; k < 4; k++) s[3 + k] = fmaf(__fadd_rn(o[k], ep.b3[k]), p.dt, s[3 + k]);
+    for (int k = 0; k < 4; k++) s[3 + k] = fmaf(__fadd_rn(o[k], ep.b_last[k]), p.dt, s[3 + k]);
     if (fabsf(s[3]) >= 1.57f) crash = 1;  // getCrash, PI/costs.cu:301-305
   }
 
@@ -418,29 +443,56 @@ __global__ void __launch_bounds__(TILE, 8) rollout_tc_kernel(const __grid_consta
   if ((tid & 31) == 0 && wbest != 0xffffffffu) atomicMin(p.baseline + wctrl, wbest);
   fence_before();
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(G::TMEM_COLS) : "memory");
 }
 
 }  // namespace tc
 
-cudaError_t launch_rollout_nn32_tc(const RolloutParams &p, cudaStream_t st, const float *host_theta_t) {
+template <int HID, int NHID>
+static cudaError_t launch_tc(const RolloutParams &p, cudaStream_t st, const float *host_theta_t) {
+  using G = tc::Geo<HID, NHID>;
   const long long total = (long long)p.B * p.n_local;
   const unsigned grid = (unsigned)((total + tc::TILE - 1) / tc::TILE);
-  tc::TcEpilogue ep;
-  // theta_t: Wt1[6][32] b1[32] Wt2[32][32] b2[32] Wt3[32][4] b3[4]; the folded biases are b + rowsum(W) (tanh = 1 - 2r)
-  for (int j = 0; j < 32; j++) {
-    double s2 = host_theta_t[1248 + j];
-    for (int k = 0; k < 32; k++) s2 += (double)host_theta_t[224 + k * 32 + j];
-    ep.eb1[j] = (float)std::exp(2.0 * (double)host_theta_t[192 + j]);
-    ep.eb2[j] = (float)std::exp(2.0 * s2);
-  }
+  // the folded biases are b + rowsum(W) (tanh = 1 - 2r travels as r); theta_t holds Wt[k][j] per layer, then b[j]
+  tc::TcEpilogue<HID, NHID> ep;
+  for (int j = 0; j < HID; j++) ep.eb[0][j] = (float)std::exp(2.0 * (double)host_theta_t[G::TH_B1 + j]);
+  for (int h = 1; h < NHID; h++)
+    for (int j = 0; j < HID; j++) {
+      double sum = host_theta_t[G::th_b(h) + j];
+      for (int k = 0; k < HID; k++) sum += (double)host_theta_t[G::th_w(h) + k * HID + j];
+      ep.eb[h][j] = (float)std::exp(2.0 * sum);
+    }
   for (int j = 0; j < 4; j++) {
-    double s3 = host_theta_t[1408 + j];
-    for (int k = 0; k < 32; k++) s3 += (double)host_theta_t[1280 + k * 4 + j];
-    ep.b3[j] = (float)s3;
+    double sum = host_theta_t[G::TH_BL + j];
+    for (int k = 0; k < HID; k++) sum += (double)host_theta_t[G::TH_WL + k * 4 + j];
+    ep.b_last[j] = (float)sum;
   }
-  tc::rollout_tc_kernel<<<grid, tc::TILE, tc::SMEM_PAD_BYTES, st>>>(p, ep);
+  if (G::SMEM_BYTES > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(tc::rollout_tc_kernel<HID, NHID>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+  }
+  tc::rollout_tc_kernel<HID, NHID><<<grid, tc::TILE, G::SMEM_BYTES, st>>>(p, ep);
   return cudaGetLastError();
+}
+
+cudaError_t launch_rollout_nn32_tc(const RolloutParams &p, cudaStream_t st, const float *host_theta_t) { return launch_tc<32, 2>(p, st, host_theta_t); }
+cudaError_t launch_rollout_nn64_tc(const RolloutParams &p, cudaStream_t st, const float *host_theta_t) { return launch_tc<64, 4>(p, st, host_theta_t); }
+
+// True when every folded bias of the network keeps e^(2 b) inside the FP32 range (|b| < 40); otherwise the caller uses
+// the FP32 kernels.  widths = {6, HID x NHID, 4}.
+bool tc_biases_in_range(const float *host_theta_t, int hid, int nhid) {
+  const int th_b1 = 6 * hid;
+  for (int j = 0; j < hid; j++)
+    if (!(std::fabs(host_theta_t[th_b1 + j]) < 40.0f)) return false;
+  for (int h = 1; h < nhid; h++) {
+    const int w = 7 * hid + (h - 1) * (hid * hid + hid), b = w + hid * hid;
+    for (int j = 0; j < hid; j++) {
+      double sum = host_theta_t[b + j];
+      for (int k = 0; k < hid; k++) sum += (double)host_theta_t[w + k * hid + j];
+      if (!(std::fabs(sum) < 40.0)) return false;
+    }
+  }
+  return true;
 }
 
 }  // namespace mppi

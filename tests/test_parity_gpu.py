@@ -106,8 +106,19 @@ def test_bf_2560x100_matches_oracle(models, costmap):
     check_pair(want, got, cost_tol=2e-4)
 
 
-def test_wider_deeper_network(models, costmap):
-    want, got = run_pair("nn", models, costmap, 256, T=60, tag="wider_deeper", negate=False)
+@pytest.mark.parametrize("variant", [0, 1])
+def test_wider_deeper_network(models, costmap, variant):
+    """6-64-64-64-64-4 (SRC/params/models/wider_deeper_network_08_20_2020.npz): AUTO runs it on the tensor-core kernel
+    (rollout_tc_kernel<64, 4>), variant 1 on the one-rollout-per-thread FP32 kernel."""
+    want, got = run_pair("nn", models, costmap, 256, T=60, tag="wider_deeper", negate=False, variant=variant)
+    check_pair(want, got, cost_tol=3e-4)
+    cp = cost_params_for(costmap)
+    with make_context("nn", models, costmap, cp, 256, tag="wider_deeper", negate_yaw_der=False, variant=variant) as ctx:
+        assert ctx.resolved_variant() == (10 if variant == 0 else 1)
+
+
+def test_wider_deeper_network_1920x100_tensor_kernel(models, costmap):
+    want, got = run_pair("nn", models, costmap, 1920, T=100, tag="wider_deeper", negate=False, speed=4.0, scenario="top")
     check_pair(want, got, cost_tol=3e-4)
 
 
