@@ -376,6 +376,8 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ F
   float *act = Usm + 2 * T;          // [2][FIN_MAX_WIDTH]
   float *sw = act + 2 * FIN_MAX_WIDTH;  // staged parameters
   __shared__ float rec_sm[4 + 2 * 256 + 4];  // the combined record (combine_partials; T <= 256)
+  __shared__ int ns_sm[16];                 // layer widths of the runtime-layer network
+  if (tid < 16 && tid < p.num_layers) ns_sm[tid] = p.net_structure[tid];
   __shared__ float scale[64];
   __shared__ float hdr[4];
   float *inbox = p.inbox + (size_t)b * p.inbox_stride;
@@ -493,19 +495,34 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ F
     if (lane == 0) { csol[2 * i] = u0; csol[2 * i + 1] = u1; }
     float dyn[4];
     if (p.num_layers > 0) {
-      // lane j computes neurons j, j+32, ... of each layer; activations ping-pong through smem
+      // runtime-layer MLP (the 6-64-64-64-64-4 network): lane j owns neurons j and j + 32 of each layer, four interleaved
+      // partial sums each (FMA, tanh_fast: the arithmetic of WarpMlp32, inside the 1e-4 tolerance of the host twin);
+      // activations ping-pong through shared memory, weights are staged there once per launch
       float *cur = act, *nxt = act + FIN_MAX_WIDTH;
       if (lane == 0) { cur[0] = s[3]; cur[1] = s[4]; cur[2] = s[5]; cur[3] = s[6]; cur[4] = u0; cur[5] = u1; }
       __syncwarp();
       const float *W = sw;
       for (int l = 0; l + 1 < p.num_layers; l++) {
-        const int nin = p.net_structure[l], nout = p.net_structure[l + 1];
-        for (int j = lane; j < nout; j += 32) {
-          float t = 0.0f;
-          for (int k = 0; k < nin; k++) t = __fadd_rn(t, __fmul_rn(W[k * nout + j], cur[k]));
-          t = __fadd_rn(t, W[nin * nout + j]);
-          if (l + 2 < p.num_layers) t = tanhf(t);
-          nxt[j] = t;
+        const int nin = ns_sm[l], nout = ns_sm[l + 1];
+        for (int j0 = lane; j0 < nout; j0 += 64) {
+          const int j1 = j0 + 32;
+          const bool two = j1 < nout;
+          const float *w0 = W + j0, *w1 = W + (two ? j1 : j0);
+          float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f, c0 = 0.0f, c1 = 0.0f, c2 = 0.0f, c3 = 0.0f;
+          int k = 0;
+          for (; k + 3 < nin; k += 4) {
+            const float4 x = *reinterpret_cast<const float4 *>(cur + k);
+            a0 = fmaf(w0[(k + 0) * nout], x.x, a0); a1 = fmaf(w0[(k + 1) * nout], x.y, a1);
+            a2 = fmaf(w0[(k + 2) * nout], x.z, a2); a3 = fmaf(w0[(k + 3) * nout], x.w, a3);
+            c0 = fmaf(w1[(k + 0) * nout], x.x, c0); c1 = fmaf(w1[(k + 1) * nout], x.y, c1);
+            c2 = fmaf(w1[(k + 2) * nout], x.z, c2); c3 = fmaf(w1[(k + 3) * nout], x.w, c3);
+          }
+          for (; k < nin; k++) { a0 = fmaf(w0[k * nout], cur[k], a0); c0 = fmaf(w1[k * nout], cur[k], c0); }
+          float t0 = ((a0 + a1) + (a2 + a3)) + w0[nin * nout];
+          float t1 = ((c0 + c1) + (c2 + c3)) + w1[nin * nout];
+          if (l + 2 < p.num_layers) { t0 = tanh_fast(t0); t1 = tanh_fast(t1); }
+          nxt[j0] = t0;
+          if (two) nxt[j1] = t1;
         }
         __syncwarp();
         W += (nin + 1) * nout;
