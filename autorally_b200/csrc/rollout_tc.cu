@@ -44,6 +44,15 @@ namespace tc {
 #ifndef TC_EXP
 #define TC_EXP 0  // timing experiments only (tools/exp_tc_parts.sh); 0 = the product kernel
 #endif
+#ifndef TC_MINCTAS
+#define TC_MINCTAS 8  // resident tiles per SM of the 32-wide kernel (registers per thread = 65536 / 128 / TC_MINCTAS)
+#endif
+#ifndef TC_PAD
+#define TC_PAD 0      // 1: pad the dynamic shared memory so that at most MIN_CTAS CTAs are resident (experiment)
+#endif
+#ifndef TC_DUAL
+#define TC_DUAL 0     // 1: two 16-column epilogue chunks in flight
+#endif
 
 constexpr int TILE = 128;         // rollouts per CTA = TMEM lanes
 constexpr float TANH_SCALE = 2.88539008177792681472f;  // 2 log2(e)
@@ -69,8 +78,14 @@ struct Geo {
   static constexpr int B_BYTES = OFF_BL + 2 * SZ_BL;
   // HID = 32: the pad keeps residency at 8 CTAs per SM (8 x 64 TMEM columns): a ninth CTA would only spin in
   // tcgen05.alloc.  HID = 64: 56 KB of weights, 3 CTAs per SM (4 x 128 columns would fit, shared memory does not).
-  static constexpr int SMEM_BYTES = B_BYTES < 24 * 1024 ? 24 * 1024 : B_BYTES;
-  static constexpr int MIN_CTAS = HID == 32 ? 8 : 3;
+  // Resident tiles per SM: 8 x 64 TMEM columns at HID = 32 (the 64 registers per thread this allows fill the register
+  // file exactly, so a ninth CTA, which could only spin in tcgen05.alloc, never becomes resident); 3 at HID = 64 (56 KB of
+  // weights each).  No shared-memory padding: padding the allocation to fence off extra CTAs costs L1 / texture cache
+  // (unified with shared memory) and was measured 8 % slower at 1 M rollouts (profiles/exp_tc_cfg_r01.txt).  The launcher
+  // falls back to PAD_BYTES only if a build ever uses so few registers that one more CTA would fit.
+  static constexpr int MIN_CTAS = HID == 32 ? TC_MINCTAS : 3;
+  static constexpr int PAD_BYTES = (227 / MIN_CTAS - 2) * 1024;
+  static constexpr int SMEM_BYTES = (TC_PAD && B_BYTES < PAD_BYTES) ? PAD_BYTES : B_BYTES;
   // packed transposed parameters: per layer Wt[k][j] then b[j]
   static constexpr int TH_W1 = 0, TH_B1 = 6 * HID;
   __host__ __device__ static constexpr int th_w(int h) { return 7 * HID + (h - 1) * (HID * HID + HID); }       // hidden layer h >= 1
@@ -363,6 +378,20 @@ rollout_tc_kernel(const __grid_constant__ RolloutParams p, const __grid_constant
     // ---- following layers: tanh epilogue -> hi / lo activations back into TMEM -> 3 MMAs per K = 16 chunk ----
 #pragma unroll
     for (int layer = 1; layer <= NHID; layer++) {  // layer = index of the layer whose MMAs are issued here (NHID = output layer)
+#if TC_DUAL
+#pragma unroll
+      for (int c = 0; c < G::NCH; c += 2) {  // experiment: two chunks in flight (needs ~16 more registers)
+        float v0[16], v1[16];
+        uint32_t h[16];
+        tmem_ld16(lane_base + G::COL_D + 16 * c, v0);
+        tmem_ld16(lane_base + G::COL_D + 16 * c + 16, v1);
+        wait_ld();
+        activate16(v0, &ep.eb[layer - 1][16 * c], h);
+        tmem_st16(lane_base + G::COL_A + 16 * c, h);
+        activate16(v1, &ep.eb[layer - 1][16 * c + 16], h);
+        tmem_st16(lane_base + G::COL_A + 16 * c + 16, h);
+      }
+#else
 #pragma unroll
       for (int c = 0; c < G::NCH; c++) {
         float v[16];
@@ -372,6 +401,7 @@ rollout_tc_kernel(const __grid_constant__ RolloutParams p, const __grid_constant
         activate16(v, &ep.eb[layer - 1][16 * c], h);
         tmem_st16(lane_base + G::COL_A + 16 * c, h);
       }
+#endif
       wait_st();
       fence_before();
       if (TC_EXP != 4) __syncthreads();
@@ -467,11 +497,23 @@ static cudaError_t launch_tc(const RolloutParams &p, cudaStream_t st, const floa
     for (int k = 0; k < HID; k++) sum += (double)host_theta_t[G::TH_WL + k * 4 + j];
     ep.b_last[j] = (float)sum;
   }
-  if (G::SMEM_BYTES > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(tc::rollout_tc_kernel<HID, NHID>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
+  static int smem_bytes = 0;  // decided once per instantiation
+  if (smem_bytes == 0) {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, tc::rollout_tc_kernel<HID, NHID>);
     if (e != cudaSuccess) return e;
+    int bytes = G::SMEM_BYTES;
+    const long long tmem_tiles = 512 / G::TMEM_COLS;
+    const bool regs_admit_more = (long long)fa.numRegs * tc::TILE * (tmem_tiles + 1) <= 65536;
+    const bool smem_admits_more = (long long)(bytes + 2048) * (tmem_tiles + 1) <= 228 * 1024;
+    if (regs_admit_more && smem_admits_more) bytes = ((228 / (int)(tmem_tiles + 1)) - 1) * 1024;  // keep TMEM the only limiter
+    if (bytes > 48 * 1024) {
+      e = cudaFuncSetAttribute(tc::rollout_tc_kernel<HID, NHID>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+      if (e != cudaSuccess) return e;
+    }
+    smem_bytes = bytes;
   }
-  tc::rollout_tc_kernel<HID, NHID><<<grid, tc::TILE, G::SMEM_BYTES, st>>>(p, ep);
+  tc::rollout_tc_kernel<HID, NHID><<<grid, tc::TILE, smem_bytes, st>>>(p, ep);
   return cudaGetLastError();
 }
 

@@ -97,3 +97,28 @@ def test_cost_param_struct_layout_matches_the_header():
     assert ctypes.sizeof(params.CostParamsStruct) == 4 * (11 + 2 + 9 + 1)
     s = params.CostParams().to_struct()
     assert abs(s.desired_speed - 8.0) < 1e-7 and abs(s.boundary_threshold - 0.65) < 1e-7 and s.l1_cost == 0
+
+
+def test_sampler_fast_division_constants_are_exact():
+    """weighting.cuh FastDiv: with s = ceil(log2 d) and M = ceil(2^(31+s) / d), (n * M) >> (31 + s) == n // d for every
+    n < 2^31 (the sampler divides its flat float4 index by T/2 and by the rollout count this way)."""
+    import random
+
+    def make(d):
+        if d <= 1:
+            return 0, 0
+        s = 0
+        while (1 << s) < d:
+            s += 1
+        return ((1 << (31 + s)) + d - 1) // d, s - 1
+
+    rng = random.Random(5)
+    divisors = list(range(1, 130)) + [50, 1000, 1920, 2560, 4096, 65536, 524288, 1048576, 999983, (1 << 20) + 1, 1 << 30, (1 << 31) - 1]
+    for d in divisors:
+        mul, shift = make(d)
+        assert mul < 1 << 32
+        probes = [0, 1, d - 1, d, d + 1, 2 * d - 1, (1 << 31) - 1, (1 << 31) - 2] + [rng.randrange(1 << 31) for _ in range(500)]
+        for n in probes:
+            if 0 <= n < 1 << 31:
+                q = (((n * mul) >> 32) >> shift) if mul else n
+                assert q == n // d, (d, n)

@@ -344,3 +344,16 @@ def test_1m_rollouts_tensor_and_ffma2_kernels_agree(models, costmap):
     assert rel_err(a["normalizer"], b["normalizer"]).max() < 1e-3
     assert rel_err(a["U"], b["U"]).max() < 1e-4
     assert rel_err(a["state_solution"], b["state_solution"]).max() < 1e-4
+
+
+def test_tensor_kernel_declines_networks_whose_folded_biases_leave_fp32_range(models, costmap):
+    """rollout_tc.cu folds the biases into e^(2 b) constants; a network with |b| >= 40 must run on the FP32 kernels."""
+    cp = cost_params_for(costmap)
+    theta = models["autorally_nnet_theta"].copy()
+    theta[6 * 32 + 3] = 45.0          # b1[3]
+    with make_context("nn", models, costmap, cp, 65536) as ctx:
+        assert ctx.resolved_variant() == 10
+        ctx.set_nn_params(theta, models["autorally_nnet_structure"])
+        assert ctx.resolved_variant() == 2
+        out = ctx.compute_control(top_state(4.0), straight_controls(100))
+        assert np.isfinite(out["U"]).all()
