@@ -50,9 +50,6 @@ namespace tc {
 #ifndef TC_PAD
 #define TC_PAD 0      // 1: pad the dynamic shared memory so that at most MIN_CTAS CTAs are resident (experiment)
 #endif
-#ifndef TC_DUAL
-#define TC_DUAL 0     // 1: two 16-column epilogue chunks in flight
-#endif
 
 constexpr int TILE = 128;         // rollouts per CTA = TMEM lanes
 constexpr float TANH_SCALE = 2.88539008177792681472f;  // 2 log2(e)
@@ -173,12 +170,18 @@ __device__ __forceinline__ void tmem_ld4(uint32_t addr, float (&v)[4]) {
   for (int i = 0; i < 4; i++) v[i] = __uint_as_float(r[i]);
 }
 
-// x0, x1 -> packed FP16 pair of the high parts (x0 in the low half = the smaller k) and of the residuals
+// x0, x1 -> packed FP16 pair of the high parts (x0 in the low half = the smaller k) and of the residuals x - hi.
+// The residual is one mixed-precision FMA per element (fma.rn.f32.f16: hi * (-1) + x, SASS FHFMA; exact, because x - hi is
+// representable): 4 instructions per pair instead of 5 with a conversion back to FP32 and a packed subtract.
 __device__ __forceinline__ void split2(float x0, float x1, uint32_t &hi, uint32_t &lo) {
   const __half2 h = __floats2half2_rn(x0, x1);
-  const float2 f = __half22float2(h);
-  const __half2 l = __floats2half2_rn(__fsub_rn(x0, f.x), __fsub_rn(x1, f.y));
   hi = *reinterpret_cast<const uint32_t *>(&h);
+  float l0, l1;
+  asm("{\n\t.reg .b16 h0, h1, m1;\n\tmov.b32 {h0, h1}, %2;\n\tmov.b16 m1, 0xBC00;\n\t"
+      "fma.rn.f32.f16 %0, h0, m1, %3;\n\tfma.rn.f32.f16 %1, h1, m1, %4;\n\t}\n"
+      : "=f"(l0), "=f"(l1)
+      : "r"(hi), "f"(x0), "f"(x1));
+  const __half2 l = __floats2half2_rn(l0, l1);
   lo = *reinterpret_cast<const uint32_t *>(&l);
 }
 
@@ -211,21 +214,18 @@ __device__ __forceinline__ void recip4(float x0, float x1, float x2, float x3, f
   r23 = __fmul2_rn(iq, d01);                               // (1 / d2, 1 / d3)
 }
 
-__device__ __forceinline__ void split2v(float2 y, uint32_t &hi, uint32_t &lo) {
-  const __half2 h = __floats2half2_rn(y.x, y.y);
-  const float2 f = __half22float2(h);
-  const float2 d = __fadd2_rn(y, make_float2(-f.x, -f.y));
-  const __half2 l = __floats2half2_rn(d.x, d.y);
-  hi = *reinterpret_cast<const uint32_t *>(&h);
-  lo = *reinterpret_cast<const uint32_t *>(&l);
-}
+__device__ __forceinline__ void split2v(float2 y, uint32_t &hi, uint32_t &lo) { split2(y.x, y.y, hi, lo); }
 
-// 16 pre-activations -> 8 columns of hi pairs, 8 columns of lo pairs
+// 16 pre-activations -> 8 columns of hi pairs, 8 columns of lo pairs.  BIAS_IN_ACC: the bias arrived through the MMA
+// (layer 1 carries it in its K padding), so 2^x needs no factor: d = 2^x + 1 and no constants are fetched.
+template <bool BIAS_IN_ACC>
 __device__ __forceinline__ void activate16(const float (&v)[16], const float *eb, uint32_t (&out)[16]) {
 #pragma unroll
   for (int j = 0; j < 4; j++) {
     float2 y01, y23;
-    recip4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3], make_float2(eb[4 * j], eb[4 * j + 1]), make_float2(eb[4 * j + 2], eb[4 * j + 3]), y01, y23);
+    const float2 e01 = BIAS_IN_ACC ? make_float2(1.0f, 1.0f) : make_float2(eb[4 * j], eb[4 * j + 1]);
+    const float2 e23 = BIAS_IN_ACC ? make_float2(1.0f, 1.0f) : make_float2(eb[4 * j + 2], eb[4 * j + 3]);
+    recip4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3], e01, e23, y01, y23);
     split2v(y01, out[2 * j], out[8 + 2 * j]);
     split2v(y23, out[2 * j + 1], out[8 + 2 * j + 1]);
   }
@@ -258,6 +258,8 @@ rollout_tc_kernel(const __grid_constant__ RolloutParams p, const __grid_constant
       put_split(smem + G::OFF_B1A, smem + G::OFF_B1B, HID, n, k, w);
       put_split(smem + G::OFF_B1A, nullptr, HID, n, 8 + k, w);
     }
+    for (int n = tid; n < HID; n += TILE)  // b1 rides in the K padding: the operand carries 1.0 at k = 6
+      put_split(smem + G::OFF_B1A, smem + G::OFF_B1B, HID, n, 6, __fmul_rn(th[G::TH_B1 + n], TANH_SCALE));
 #pragma unroll
     for (int h = 1; h < NHID; h++) {  // hidden layer h acts on r of layer h - 1: -2 W (and the tanh scale)
       unsigned char *hi = smem + G::OFF_BH + (h - 1) * 2 * G::SZ_BH;
@@ -339,13 +341,13 @@ rollout_tc_kernel(const __grid_constant__ RolloutParams p, const __grid_constant
   float front = 0.0f, back = 0.0f;  // costmap texels under the state of the current step (requested one step ahead as well)
 
   for (int i = 0; i < p.T; i++) {
-    // ---- layer 1: a = [roll, u_x, u_y, yaw rate, steering, throttle, 0, 0] as [a_hi | a_lo], one K = 16 chunk ----
+    // ---- layer 1: a = [roll, u_x, u_y, yaw rate, steering, throttle, 1 (bias), 0] as [a_hi | a_lo], one K = 16 chunk ----
     {
       uint32_t a[8];
       split2(s[3], s[4], a[0], a[4]);
       split2(s[5], s[6], a[1], a[5]);
       a[2] = ua_hi; a[6] = ua_lo;
-      a[3] = 0u;
+      a[3] = 0x00003C00u;  // (1.0, 0): multiplies the bias row of B
       a[7] = 0u;
       tmem_st8(lane_base + G::COL_A, a);
     }
@@ -378,30 +380,16 @@ rollout_tc_kernel(const __grid_constant__ RolloutParams p, const __grid_constant
     // ---- following layers: tanh epilogue -> hi / lo activations back into TMEM -> 3 MMAs per K = 16 chunk ----
 #pragma unroll
     for (int layer = 1; layer <= NHID; layer++) {  // layer = index of the layer whose MMAs are issued here (NHID = output layer)
-#if TC_DUAL
-#pragma unroll
-      for (int c = 0; c < G::NCH; c += 2) {  // experiment: two chunks in flight (needs ~16 more registers)
-        float v0[16], v1[16];
-        uint32_t h[16];
-        tmem_ld16(lane_base + G::COL_D + 16 * c, v0);
-        tmem_ld16(lane_base + G::COL_D + 16 * c + 16, v1);
-        wait_ld();
-        activate16(v0, &ep.eb[layer - 1][16 * c], h);
-        tmem_st16(lane_base + G::COL_A + 16 * c, h);
-        activate16(v1, &ep.eb[layer - 1][16 * c + 16], h);
-        tmem_st16(lane_base + G::COL_A + 16 * c + 16, h);
-      }
-#else
 #pragma unroll
       for (int c = 0; c < G::NCH; c++) {
         float v[16];
         uint32_t h[16];
         tmem_ld16(lane_base + G::COL_D + 16 * c, v);
         wait_ld();
-        activate16(v, &ep.eb[layer - 1][16 * c], h);
+        if (layer == 1) activate16<true>(v, nullptr, h);
+        else activate16<false>(v, &ep.eb[layer - 1][16 * c], h);
         tmem_st16(lane_base + G::COL_A + 16 * c, h);
       }
-#endif
       wait_st();
       fence_before();
       if (TC_EXP != 4) __syncthreads();

@@ -1,5 +1,7 @@
 #!/bin/bash
-# Builds libmppi_b200 variants of the tensor-core kernel's occupancy / ILP trade-off: name:flags pairs.
+# Builds libmppi_b200 variants of the tensor-core kernel's occupancy trade-off: name:flags pairs, flags from
+# -DTC_MINCTAS=n (resident tiles per SM) and -DTC_PAD=1 (pad shared memory to exactly that residency).  The two-chunks-in-flight
+# variant (TC_DUAL) measured in profiles/exp_tc_cfg_r01.txt was removed after the measurement.
 set -e
 cd "$(dirname "$0")/.."
 L=autorally_b200/lib; mkdir -p $L/exp
