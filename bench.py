@@ -269,6 +269,14 @@ def measure_other_configs(models, costmap, cp, world, rank, local_rank, barrier,
         ms, rk = ctx.run_resident(20, time_rollout=True)
         out["bf_2560x100"] = {"ms_per_step": ms / 20, "rollout_kernel_ms": rk / 20, "value": 2560 * T_STEPS * 20 / (ms * 1e-3),
                               "unit": "rollout-steps/s", "note": "per GPU, one controller"}
+    # the fork's wider / deeper dynamics network 6-64-64-64-64-4 (SRC/params/models/wider_deeper_network_08_20_2020.npz)
+    with make_context("nn", models, costmap, cp, N_ROLLOUTS, tag="wider_deeper", negate_yaw_der=False, device=local_rank) as ctx:
+        ctx.compute_control(top_state(4.0), straight_controls(T_STEPS))
+        ctx.run_resident(3)
+        ms, rk = ctx.run_resident(20, time_rollout=True)
+        out["wider_deeper_1920x100"] = {"ms_per_step": ms / 20, "rollout_kernel_ms": rk / 20, "value": N_ROLLOUTS * T_STEPS * 20 / (ms * 1e-3),
+                                        "unit": "rollout-steps/s", "variant": ctx.resolved_variant(),
+                                        "note": "per GPU, one controller; rollout_tc_kernel<64,4> (tcgen05)"}
     B_total, n = 4096, 256
     b0, B = controller_shard(rank, world, B_total)
     states = ellipse_states(B_total)[b0:b0 + B]
