@@ -235,6 +235,7 @@ cudaError_t launch_finalize(mppi_ctx *c, const float *gathered, int G, int last_
   p.net_structure = c->d_net_structure;
   p.num_layers = c->cfg.dynamics == MPPI_DYNAMICS_BF ? 0 : (int)c->net_structure.size();
   p.is_nn32 = (c->cfg.dynamics == MPPI_DYNAMICS_NN && c->net_kind == 32) ? 1 : 0;
+  p.is_nn64 = (c->cfg.dynamics == MPPI_DYNAMICS_NN && c->net_kind == 64) ? 1 : 0;
   p.G = G; p.B = c->B; p.T = c->T; p.shard_floats = c->shard_floats; p.inbox_stride = c->inbox_stride;
   p.outbox_stride = c->outbox_stride; p.gamma = c->gamma; p.dt = c->dt;
   p.lo0 = c->ranges[0]; p.hi0 = c->ranges[1]; p.lo1 = c->ranges[2]; p.hi1 = c->ranges[3];
@@ -245,7 +246,11 @@ cudaError_t launch_finalize(mppi_ctx *c, const float *gathered, int G, int last_
   c->launches++;
   // after an NCCL exchange (gathered != own shard) the predecessor is not one of our kernels: plain launch
   // many batched controllers: small CTAs, so that more of the single-warp nominal trajectories are resident per SM
-  return launch_pdl(c, finalize_kernel, dim3(c->B), c->B >= 64 ? 64 : 256, finalize_smem(c), c->pdl && (gathered == c->d_shard || p.combine_partials > 0), p);
+  const bool pdl = c->pdl && (gathered == c->d_shard || p.combine_partials > 0);
+  const int threads = c->B >= 64 ? 64 : 256;
+  if (p.is_nn32) return launch_pdl(c, finalize_kernel<32>, dim3(c->B), threads, finalize_smem(c), pdl, p);
+  if (p.is_nn64 && threads == 256) return launch_pdl(c, finalize_kernel<64>, dim3(c->B), threads, finalize_smem(c), pdl, p);
+  return launch_pdl(c, finalize_kernel<0>, dim3(c->B), threads, finalize_smem(c), pdl, p);
 }
 
 int check_ready(const mppi_ctx *c) {
@@ -432,7 +437,11 @@ static int upload_theta(mppi_ctx *c) {
   CK(cudaMemset(c->d_theta_t, 0, bytes));
   CK(cudaMemcpy(c->d_theta_t, c->theta_t.data(), c->theta_t.size() * sizeof(float), cudaMemcpyHostToDevice));
   const size_t fsm = finalize_smem(c);
-  if (fsm > 48 * 1024) CK(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+  if (fsm > 48 * 1024) {
+    CK(cudaFuncSetAttribute(finalize_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+    CK(cudaFuncSetAttribute(finalize_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+    CK(cudaFuncSetAttribute(finalize_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+  }
   c->have_model = true;
   return MPPI_OK;
 }

@@ -284,6 +284,7 @@ struct FinalizeParams {
   // ONE controller (B == 1, G == 1); this kernel adds them up in the fixed order of sum_partials_fixed_order, which
   // spares the weighting kernel its fence / atomic-ticket / last-CTA pass (three dependent L2 round trips)
   int combine_partials;
+  int is_nn64;  // 6-64-64-64-64-4 with 256 threads: CtaMlp<64, 4> (weights in registers)
   float *inbox;           // [B][inbox_stride]  (U is rewritten for the next iteration / resident step)
   float *outbox;          // [B][outbox_stride]: result[4] | U_smoothed[2T] | U_new[2T] | state_sol[7T] | ctrl_sol[2T]
   const float *theta_t;   // NN: transposed packed weights; BF: theta 4x25
@@ -363,11 +364,178 @@ __device__ __forceinline__ void nominal_traj_nn32(const WarpMlp32 &net, const fl
   }
 }
 
+// Nominal trajectory for a 6 -> W x NH (tanh) -> 4 network of compile-time shape (the fork's 6-64-64-64-64-4) on a
+// 256-thread CTA with the weights in REGISTERS: thread (j, g) = (tid mod W, tid / W) holds, of every hidden layer, the
+// weights of neuron j for the g-th quarter of its inputs (W/4 per layer) and sums that quarter with four interleaved FMA
+// chains; the quarters meet in shared memory, threads 0..W-1 add them in a fixed order, add the bias and apply tanh_fast.
+// Per layer the dependent chain is 4 broadcast LDS.128, W/16 FMAs deep, and two CTA barriers.  Only roll, u_x, u_y and the
+// yaw rate feed the network, so every thread integrates those four (identical arithmetic, no broadcast) while thread 0 alone
+// integrates x, y, yaw (precise sinf / cosf) and writes the solution.  Same arithmetic class as WarpMlp32.
+template <int W, int NH>
+struct CtaMlp {
+  static_assert(W == 64, "one neuron per thread of a 64-thread group, four input quarters over 256 threads");
+  static constexpr int Q = W / 4;
+  static constexpr int TH_B1 = 6 * W;
+  __host__ __device__ static constexpr int th_w(int h) { return 7 * W + (h - 1) * (W * W + W); }
+  static constexpr int TH_WL = 7 * W + (NH - 1) * (W * W + W), TH_BL = TH_WL + 4 * W;
+  float w1[6], wh[NH - 1][Q], wl[Q], b[NH], bl[4];
+
+  __device__ __forceinline__ void load(const float *__restrict__ th, int j, int g) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) w1[k] = th[k * W + j];
+    b[0] = th[TH_B1 + j];
+#pragma unroll
+    for (int h = 1; h < NH; h++) {
+#pragma unroll
+      for (int i = 0; i < Q; i++) wh[h - 1][i] = th[th_w(h) + (g * Q + i) * W + j];
+      b[h] = th[th_w(h) + W * W + j];
+    }
+#pragma unroll
+    for (int i = 0; i < Q; i++) wl[i] = th[TH_WL + (g * Q + i) * 4 + (j & 3)];
+#pragma unroll
+    for (int k = 0; k < 4; k++) bl[k] = th[TH_BL + k];
+  }
+
+  __device__ __forceinline__ static float dot_quarter(const float (&w)[Q], const float *__restrict__ x) {
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+#pragma unroll
+    for (int i = 0; i < Q; i += 4) {
+      const float4 v = *reinterpret_cast<const float4 *>(x + i);
+      a0 = fmaf(w[i], v.x, a0); a1 = fmaf(w[i + 1], v.y, a1); a2 = fmaf(w[i + 2], v.z, a2); a3 = fmaf(w[i + 3], v.w, a3);
+    }
+    return (a0 + a1) + (a2 + a3);
+  }
+
+  // act: [2][W] activations, part: [4][W] partial sums (shared memory).  All 256 threads call this.
+  __device__ __forceinline__ void trajectory(const float *__restrict__ inbox, const float *__restrict__ Usm, int T, float dt, int negate_yaw,
+                                             float lo0, float hi0, float lo1, float hi1, float *__restrict__ ssol,
+                                             float *__restrict__ csol, float *__restrict__ act, float *__restrict__ part, int tid) const {
+    const int j = tid % W, g = tid / W;
+    float x = inbox[INBOX_STATE + 0], y = inbox[INBOX_STATE + 1], yaw = inbox[INBOX_STATE + 2];
+    float roll = inbox[INBOX_STATE + 3], vx = inbox[INBOX_STATE + 4], vy = inbox[INBOX_STATE + 5], wz = inbox[INBOX_STATE + 6];
+    for (int i = 0; i < T; i++) {
+      float u0 = Usm[2 * i], u1 = Usm[2 * i + 1];
+      u0 = u0 < lo0 ? lo0 : (u0 > hi0 ? hi0 : u0);
+      u1 = u1 < lo1 ? lo1 : (u1 > hi1 ? hi1 : u1);
+      if (tid == 0) {
+        float *o = ssol + (size_t)i * S_DIM;
+        o[0] = x; o[1] = y; o[2] = yaw; o[3] = roll; o[4] = vx; o[5] = vy; o[6] = wz;
+        csol[2 * i] = u0; csol[2 * i + 1] = u1;
+        float sn, cs;
+        sincosf(yaw, &sn, &cs);
+        x = fmaf(fmaf(cs, vx, -__fmul_rn(sn, vy)), dt, x);
+        y = fmaf(fmaf(sn, vx, __fmul_rn(cs, vy)), dt, y);
+      }
+      yaw = fmaf(negate_yaw ? -wz : wz, dt, yaw);
+      // layer 1 (6 inputs, straight from registers; k ascending, bias last)
+      if (g == 0) {
+        float t = w1[0] * roll;
+        t = fmaf(w1[1], vx, t); t = fmaf(w1[2], vy, t); t = fmaf(w1[3], wz, t); t = fmaf(w1[4], u0, t); t = fmaf(w1[5], u1, t);
+        act[j] = tanh_fast(t + b[0]);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int h = 1; h < NH; h++) {
+        const float *cur = act + ((h - 1) & 1) * W;
+        float *nxt = act + (h & 1) * W;
+        part[g * W + j] = dot_quarter(wh[h - 1], cur + g * Q);
+        __syncthreads();
+        if (g == 0) nxt[j] = tanh_fast((((part[j] + part[W + j]) + (part[2 * W + j] + part[3 * W + j]))) + b[h]);
+        __syncthreads();
+      }
+      // output layer: threads j < 4 of every quarter, then every thread adds the quarters itself
+      const float *last = act + ((NH - 1) & 1) * W;
+      if (j < 4) part[g * W + j] = dot_quarter(wl, last + g * Q);
+      __syncthreads();
+      const float o0 = ((part[0] + part[W + 0]) + (part[2 * W + 0] + part[3 * W + 0])) + bl[0];
+      const float o1 = ((part[1] + part[W + 1]) + (part[2 * W + 1] + part[3 * W + 1])) + bl[1];
+      const float o2 = ((part[2] + part[W + 2]) + (part[2 * W + 2] + part[3 * W + 2])) + bl[2];
+      const float o3 = ((part[3] + part[W + 3]) + (part[2 * W + 3] + part[3 * W + 3])) + bl[3];
+      roll = fmaf(o0, dt, roll); vx = fmaf(o1, dt, vx); vy = fmaf(o2, dt, vy); wz = fmaf(o3, dt, wz);
+      __syncthreads();  // the partial sums are consumed before the next step overwrites them
+    }
+  }
+};
+
+// Nominal trajectory for a runtime-layer network (the fork's 6-64-64-64-64-4) on the WHOLE CTA: thread (j, g) = (tid mod
+// 64, tid / 64) sums the g-th slice of the inputs of neuron j (four interleaved FMA partial sums), the slices meet in
+// shared memory and threads 0..63 add them in a fixed order, add the bias and apply tanh_fast.  One warp alone issued the
+// 2 480 instructions of a timestep back to back (3.2 us per step, 0.32 ms per trajectory); spread over 8 warps the chain
+// per layer is 16 FMAs and two CTA barriers.  Every thread integrates its own copy of the state (identical arithmetic),
+// so nothing but the activations crosses threads.  Same arithmetic class as WarpMlp32 (FMA, partial sums, tanh_fast).
+__device__ __forceinline__ void nominal_traj_mlp_cta(const float *__restrict__ sw, const int *__restrict__ ns, int num_layers,
+                                                     const float *__restrict__ inbox, const float *__restrict__ Usm, int T, float dt,
+                                                     int negate_yaw, float lo0, float hi0, float lo1, float hi1,
+                                                     float *__restrict__ ssol, float *__restrict__ csol, float *__restrict__ act,
+                                                     float *__restrict__ part /* [4][64] */, int tid, int nthr) {
+  const int jl = tid & 63, g = tid >> 6, ng = nthr >= 256 ? 4 : 1, lg = nthr >= 256 ? 2 : 0;
+  const bool worker = tid < ng * 64;
+  float s[S_DIM];
+  for (int k = 0; k < S_DIM; k++) s[k] = inbox[INBOX_STATE + k];
+  for (int i = 0; i < T; i++) {
+    float u0 = Usm[2 * i], u1 = Usm[2 * i + 1];
+    u0 = u0 < lo0 ? lo0 : (u0 > hi0 ? hi0 : u0);
+    u1 = u1 < lo1 ? lo1 : (u1 > hi1 ? hi1 : u1);
+    float *cur = act, *nxt = act + FIN_MAX_WIDTH;
+    if (tid == 0) {
+#pragma unroll
+      for (int k = 0; k < S_DIM; k++) ssol[i * S_DIM + k] = s[k];
+      csol[2 * i] = u0; csol[2 * i + 1] = u1;
+      cur[0] = s[3]; cur[1] = s[4]; cur[2] = s[5]; cur[3] = s[6]; cur[4] = u0; cur[5] = u1;
+    }
+    __syncthreads();
+    const float *W = sw;
+    for (int l = 0; l + 1 < num_layers; l++) {
+      const int nin = ns[l], nout = ns[l + 1];
+      const int per = (nin + ng - 1) >> lg, k0 = g * per, k1 = min(nin, k0 + per);  // ng is 1 or 4: no integer division
+      for (int j0 = 0; j0 < nout; j0 += 64) {
+        const int j = j0 + jl;
+        if (worker && j < nout) {
+          const float *wp = W + j + k0 * nout, *cp = cur + k0;  // walked with pointer increments (no per-load multiplies)
+          float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+          int n = k1 - k0;
+          for (; n >= 4; n -= 4, wp += 4 * nout, cp += 4) {
+            const float w0 = wp[0], w1 = wp[nout], w2 = wp[2 * nout], w3 = wp[3 * nout];
+            a0 = fmaf(w0, cp[0], a0); a1 = fmaf(w1, cp[1], a1); a2 = fmaf(w2, cp[2], a2); a3 = fmaf(w3, cp[3], a3);
+          }
+          for (; n > 0; n--, wp += nout, cp++) a0 = fmaf(wp[0], cp[0], a0);
+          part[g * 64 + jl] = (a0 + a1) + (a2 + a3);
+        }
+        __syncthreads();
+        if (tid < 64 && j < nout) {
+          float t = part[jl];
+          for (int q = 1; q < ng; q++) t += part[q * 64 + jl];
+          t += W[nin * nout + j];
+          if (l + 2 < num_layers) t = tanh_fast(t);
+          nxt[j] = t;
+        }
+        __syncthreads();
+      }
+      W += (nin + 1) * nout;
+      float *tmp = cur; cur = nxt; nxt = tmp;
+    }
+    const float o0 = cur[0], o1 = cur[1], o2 = cur[2], o3 = cur[3];
+    const float cs = cosf(s[2]), sn = sinf(s[2]);
+    const float d0 = __fsub_rn(__fmul_rn(cs, s[4]), __fmul_rn(sn, s[5]));
+    const float d1 = __fadd_rn(__fmul_rn(sn, s[4]), __fmul_rn(cs, s[5]));
+    const float d2 = negate_yaw ? -s[6] : s[6];
+    s[0] = __fadd_rn(s[0], __fmul_rn(d0, dt));
+    s[1] = __fadd_rn(s[1], __fmul_rn(d1, dt));
+    s[2] = __fadd_rn(s[2], __fmul_rn(d2, dt));
+    s[3] = __fadd_rn(s[3], __fmul_rn(o0, dt)); s[4] = __fadd_rn(s[4], __fmul_rn(o1, dt));
+    s[5] = __fadd_rn(s[5], __fmul_rn(o2, dt)); s[6] = __fadd_rn(s[6], __fmul_rn(o3, dt));
+    __syncthreads();  // everybody has read the outputs before thread 0 overwrites the input slots of the next step
+  }
+}
+
 // grid B, block 256 (64 when many controllers are batched: only warp 0 does the long part).  Combines the G shard records (log-sum-exp rescale),
 // U_new = W / Z (control update :663-667), Savitzky-Golay (:468-499), then warp 0 integrates the
 // nominal trajectory with the host-twin arithmetic (separate multiply and add, precise tanhf/sinf/cosf).
 __global__ void bump_counter_kernel(uint32_t *counter) { *counter += 1u; }
 
+// NET: 32 = NeuralNetModel<7,2,3,6,32,32,4> (WarpMlp32), 64 = 6-64-64-64-64-4 on 256 threads (CtaMlp<64,4>), 0 = anything else
+// (basis functions, runtime-layer networks).  One instantiation per kind: each carries only its own weights in registers.
+template <int NET>
 __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ FinalizeParams p) {
   extern __shared__ float fsm[];
   const int T = p.T, tid = threadIdx.x, b = blockIdx.x, nthr = blockDim.x;
@@ -384,7 +552,9 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ F
   float *outbox = p.outbox + (size_t)b * p.outbox_stride;
   // warp 0 fetches its slices of the network while the other warps combine the shard records
   WarpMlp32 net;
-  if (p.is_nn32 && p.last_iter && tid < 32) net.load(p.theta_t, tid);
+  if (NET == 32 && p.last_iter && tid < 32) net.load(p.theta_t, tid);
+  CtaMlp<64, 4> net64;
+  if (NET == 64 && p.last_iter) net64.load(p.theta_t, tid & 63, tid >> 6);
   pdl_wait();  // the shard records come from the weighting kernel (or the exchange)
   if (p.p2p_flags != nullptr) {
     if (tid < p.G) {
@@ -462,7 +632,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ F
     outbox[4 + k] = acc;
   }
   // stage the model parameters for the generic nominal trajectory (the 6-32-32-4 path holds them in registers)
-  if (!p.is_nn32) {
+  if (NET == 0) {
     int nparams = 100;
     if (p.num_layers > 0) {
       nparams = 0;
@@ -473,12 +643,25 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ F
   __syncthreads();
   if (p.feed_back)
     for (int k = tid; k < 2 * T; k += nthr) inbox[INBOX_U + k] = Usm[k];
+  if (NET == 64) {
+    __shared__ __align__(16) float act64[2 * 64];
+    __shared__ float part64[4 * 64];
+    net64.trajectory(inbox, Usm, T, p.dt, p.negate_yaw, p.lo0, p.hi0, p.lo1, p.hi1, outbox + 4 + 4 * T, outbox + 4 + 4 * T + S_DIM * T,
+                     act64, part64, tid);
+    return;
+  }
+  if (NET == 0 && p.num_layers > 0) {  // runtime-layer network: the whole CTA works on the trajectory
+    __shared__ float part_sm[4 * 64];
+    nominal_traj_mlp_cta(sw, ns_sm, p.num_layers, inbox, Usm, T, p.dt, p.negate_yaw, p.lo0, p.hi0, p.lo1, p.hi1,
+                         outbox + 4 + 4 * T, outbox + 4 + 4 * T + S_DIM * T, act, part_sm, tid, nthr);
+    return;
+  }
   if (tid >= 32) return;
   // ---- nominal trajectory (computeNominalTraj :501-519 -> host updateState) on warp 0 ----
   const int lane = tid;
   float *ssol = outbox + 4 + 4 * T;
   float *csol = ssol + S_DIM * T;
-  if (p.is_nn32) {
+  if (NET == 32) {
     nominal_traj_nn32(net, inbox, Usm, T, p.dt, p.negate_yaw, p.lo0, p.hi0, p.lo1, p.hi1, ssol, csol, act, lane);
     return;
   }
