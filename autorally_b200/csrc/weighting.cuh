@@ -536,7 +536,7 @@ __global__ void bump_counter_kernel(uint32_t *counter) { *counter += 1u; }
 // NET: 32 = NeuralNetModel<7,2,3,6,32,32,4> (WarpMlp32), 64 = 6-64-64-64-64-4 on 256 threads (CtaMlp<64,4>), 0 = anything else
 // (basis functions, runtime-layer networks).  One instantiation per kind: each carries only its own weights in registers.
 template <int NET>
-__global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ FinalizeParams p) {
+__global__ void __launch_bounds__(256, NET == 0 ? 1 : 2) finalize_kernel(const __grid_constant__ FinalizeParams p) {
   extern __shared__ float fsm[];
   const int T = p.T, tid = threadIdx.x, b = blockIdx.x, nthr = blockDim.x;
   float *Unew = fsm;                 // [2T]
