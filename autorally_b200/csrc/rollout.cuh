@@ -145,6 +145,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) rollout_kernel(const __grid_const
       pure_noise[r] = (rg >= p.pure_noise_from);
       row[r] = reinterpret_cast<float2 *>(p.du) + (size_t)(g0 + r) * p.T;
     }
+    // one rollout per thread (the latency-bound shapes: basis functions, 64-wide FP32 kernel): fetch the costmap texels a
+    // step ahead; the two-rollouts-per-thread FFMA2 kernel is register-bound and keeps the plain order
+    constexpr bool EARLY_TEXELS = (R == 1);
+    float front[R], back[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) { front[r] = 0.0f; back[r] = 0.0f; }
     for (int i = 0; i < p.T; i++) {
       const float2 Ui = U[i];
       float in[6][R];
@@ -170,26 +176,49 @@ __global__ void __launch_bounds__(BLOCK, MINB) rollout_kernel(const __grid_const
         if (i > 0) {
           // running mean of the step costs, PI/mppi_controller.cu:162-165: float difference,
           // double divide (by a tabulated reciprocal) and double accumulate, float store.
-          const float c = running_cost_step(p.cp, p.tex, s[r], u[r][0], u[r][1], du[r][0], du[r][1], p.nu0, p.nu1, crash[r]);
+          float c;
+          if (EARLY_TEXELS)
+            c = running_cost_from_parts(p.cp, step_cost_from_lookups(p.cp, front[r], back[r], s[r][4], s[r][5], u[r][0], u[r][1], du[r][0],
+                                                                      du[r][1], p.nu0, p.nu1), crash[r]);
+          else
+            c = running_cost_step(p.cp, p.tex, s[r], u[r][0], u[r][1], du[r][0], du[r][1], p.nu0, p.nu1, crash[r]);
           running[r] = (float)((double)running[r] + (double)__fsub_rn(c, running[r]) * p.inv_step[i]);
         }
         in[0][r] = s[r][3]; in[1][r] = s[r][4]; in[2][r] = s[r][5]; in[3][r] = s[r][6];
         in[4][r] = u[r][0]; in[5][r] = u[r][1];
       }
+      if (EARLY_TEXELS) {
+        // x, y, yaw do not depend on the dynamics model: they are advanced first (same operations, same order), so that the
+        // two costmap texels of the NEXT step's cost are in flight during the whole dynamics evaluation
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          float sn, cs;
+          sincosf(s[r][2], &sn, &cs);
+          const float d0 = fmaf(cs, s[r][4], -__fmul_rn(sn, s[r][5]));
+          const float d1 = fmaf(sn, s[r][4], __fmul_rn(cs, s[r][5]));
+          const float d2 = p.negate_yaw ? -s[r][6] : s[r][6];
+          s[r][0] = fmaf(d0, p.dt, s[r][0]);
+          s[r][1] = fmaf(d1, p.dt, s[r][1]);
+          s[r][2] = fmaf(d2, p.dt, s[r][2]);
+          if (i + 1 < p.T) track_lookups(p.cp, p.tex, s[r][0], s[r][1], s[r][2], front[r], back[r]);
+        }
+      }
       float dyn_out[4][R];
       DYN::deriv(sw, tsm, in, dyn_out);
 #pragma unroll
       for (int r = 0; r < R; r++) {
-        // kinematics, PI/neural_net_model.cu:346-355 (precise sinf/cosf)
-        float sn, cs;
-        sincosf(s[r][2], &sn, &cs);
-        const float d0 = fmaf(cs, s[r][4], -__fmul_rn(sn, s[r][5]));
-        const float d1 = fmaf(sn, s[r][4], __fmul_rn(cs, s[r][5]));
-        const float d2 = p.negate_yaw ? -s[r][6] : s[r][6];
-        // incrementState, PI/neural_net_model.cu:334-344
-        s[r][0] = fmaf(d0, p.dt, s[r][0]);
-        s[r][1] = fmaf(d1, p.dt, s[r][1]);
-        s[r][2] = fmaf(d2, p.dt, s[r][2]);
+        if (!EARLY_TEXELS) {
+          // kinematics, PI/neural_net_model.cu:346-355 (precise sinf/cosf)
+          float sn, cs;
+          sincosf(s[r][2], &sn, &cs);
+          const float d0 = fmaf(cs, s[r][4], -__fmul_rn(sn, s[r][5]));
+          const float d1 = fmaf(sn, s[r][4], __fmul_rn(cs, s[r][5]));
+          const float d2 = p.negate_yaw ? -s[r][6] : s[r][6];
+          // incrementState, PI/neural_net_model.cu:334-344
+          s[r][0] = fmaf(d0, p.dt, s[r][0]);
+          s[r][1] = fmaf(d1, p.dt, s[r][1]);
+          s[r][2] = fmaf(d2, p.dt, s[r][2]);
+        }
 #pragma unroll
         for (int k = 0; k < 4; k++) s[r][3 + k] = fmaf(dyn_out[k][r], p.dt, s[r][3 + k]);
         // getCrash, PI/costs.cu:301-305 (the reference compares against the double 1.57)
