@@ -151,6 +151,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) rollout_kernel(const __grid_const
     float front[R], back[R];
 #pragma unroll
     for (int r = 0; r < R; r++) { front[r] = 0.0f; back[r] = 0.0f; }
+    float2 e_next[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) e_next[r] = EARLY_TEXELS ? row[r][0] : make_float2(0.0f, 0.0f);
     for (int i = 0; i < p.T; i++) {
       const float2 Ui = U[i];
       float in[6][R];
@@ -158,7 +161,13 @@ __global__ void __launch_bounds__(BLOCK, MINB) rollout_kernel(const __grid_const
 #pragma unroll
       for (int r = 0; r < R; r++) {
         // PI/mppi_controller.cu:130-155
-        const float2 e = row[r][i];
+        float2 e;
+        if (EARLY_TEXELS) {  // one rollout per thread: the noise of the next step is requested a step ahead as well
+          e = e_next[r];
+          if (i + 1 < p.T) e_next[r] = row[r][i + 1];
+        } else {
+          e = row[r][i];
+        }
         if (noise_free[r] || i < p.opt_delay) {
           du[r][0] = 0.0f; du[r][1] = 0.0f;
           u[r][0] = Ui.x; u[r][1] = Ui.y;
