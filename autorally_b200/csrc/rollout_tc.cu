@@ -185,8 +185,8 @@ __device__ __forceinline__ void split2(float x0, float x1, uint32_t &hi, uint32_
   lo = *reinterpret_cast<const uint32_t *>(&l);
 }
 
-// Epilogue constants, in the kernel parameter block (constant bank): e^(2 b) of the first hidden layer,
-// e^(2 (b + rowsum W)) of the following ones, b + rowsum W of the output layer.
+// Epilogue constants, in the kernel parameter block (constant bank): e^(2 (b + rowsum W)) of hidden layers 2 .. NHID
+// (eb[1 ..]; the first layer's bias goes through its MMA), b + rowsum W of the output layer.
 template <int HID, int NHID>
 struct TcEpilogue {
   float eb[NHID][HID];
@@ -473,7 +473,7 @@ static cudaError_t launch_tc(const RolloutParams &p, cudaStream_t st, const floa
   const unsigned grid = (unsigned)((total + tc::TILE - 1) / tc::TILE);
   // the folded biases are b + rowsum(W) (tanh = 1 - 2r travels as r); theta_t holds Wt[k][j] per layer, then b[j]
   tc::TcEpilogue<HID, NHID> ep;
-  for (int j = 0; j < HID; j++) ep.eb[0][j] = (float)std::exp(2.0 * (double)host_theta_t[G::TH_B1 + j]);
+  for (int j = 0; j < HID; j++) ep.eb[0][j] = 1.0f;  // unused: the first layer's bias rides in the K padding of its MMA
   for (int h = 1; h < NHID; h++)
     for (int j = 0; j < HID; j++) {
       double sum = host_theta_t[G::th_b(h) + j];
