@@ -143,10 +143,11 @@ int resolve_variant(const mppi_ctx *c) {
     return (c->theta_t.size() >= 13188 && tc_biases_in_range(c->theta_t.data(), 64, 4)) ? MPPI_ROLLOUT_TENSOR : MPPI_ROLLOUT_THREAD1;
   }
   if (v == MPPI_ROLLOUT_AUTO) {
-    // Measured on B200 (profiles/exp_tc_r01.txt, rollout kernel only): one rollout per half-warp wins up to 16384 rollouts
-    // (233 us vs 280 us for the tensor-core kernel), loses from 32768 (434 us vs 335 us); the FFMA2 kernel (THREAD2) is
-    // slower than the tensor-core kernel at every size (1M rollouts: 7.2 ms vs 4.0 ms) and stays as a selectable variant.
-    if (total <= 24576) v = MPPI_ROLLOUT_HALF16;
+    // Measured on B200 (profiles/exp_tc_r01.txt, rollout kernel only): the tensor-core kernel takes 240 us up to one wave of
+    // tiles (16384 rollouts: 128 tiles, under one per SM) and grows slowly beyond it; one rollout per half-warp takes 123 us
+    // at 8192 and 232 us at 16384 rollouts, 428 us at 32768 (tensor: 270 us).  The FFMA2 kernel (THREAD2) is slower than the
+    // tensor-core kernel at every size (1M rollouts: 7.2 ms vs 3.5 ms) and stays as a selectable variant.
+    if (total <= 16384) v = MPPI_ROLLOUT_HALF16;
     else v = MPPI_ROLLOUT_TENSOR;
   }
   // the tensor-core kernel folds the hidden-layer biases into its exponentials as e^(2 b1) and e^(2 (b2 + rowsum W2))

@@ -43,7 +43,7 @@ enum {
 
 enum { MPPI_DYNAMICS_NN = 0, MPPI_DYNAMICS_BF = 1 };
 
-/* Rollout-kernel variants (mppi_config.rollout_variant).  AUTO picks by problem size: 6-32-32-4 up to 24576 rollouts
+/* Rollout-kernel variants (mppi_config.rollout_variant).  AUTO picks by problem size: 6-32-32-4 up to 16384 rollouts
  * HALF16, above TENSOR; 6-64-64-64-64-4 always TENSOR; basis functions THREAD1.  A network whose folded biases would
  * leave the FP32 range in the tensor kernel's e^(2b) constants (|b| >= 40) runs on the FP32 kernels instead. */
 enum {

@@ -276,7 +276,7 @@ def test_launch_paths_are_bitwise_equivalent(models, costmap, monkeypatch):
     assert not np.array_equal(results[0][0]["U"], results[0][1]["U"])  # fresh noise on the second call
 
 
-# ---- the tensor-core rollout kernel (MPPI_ROLLOUT_TENSOR = 10, rollout_tc.cu; AUTO above 24576 rollouts) ----
+# ---- the tensor-core rollout kernel (MPPI_ROLLOUT_TENSOR = 10, rollout_tc.cu; AUTO above 16384 rollouts) ----
 
 @pytest.mark.parametrize("N,T", [(64, 1), (64, 2), (192, 7), (320, 33), (4096, 100)])
 def test_tensor_kernel_ragged_sizes(models, costmap, N, T):
