@@ -32,7 +32,8 @@ __device__ __forceinline__ float2 box_muller(uint32_t xa, uint32_t xb) {
   // radius = sqrt(-2 ln((xa + .5) 2^-32)); angle = 2 pi (xb + .5) 2^-32 - pi
   const float ua = fmaf((float)xa, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
   const float ang = fmaf((float)xb, 1.4629180792671596e-09f, -3.14159265358979f + 7.3145903963357981e-10f);
-  const float rad = sqrtf(-2.0f * __logf(ua));
+  float rad;  // MUFU.SQRT: the IEEE sqrtf sequence (Newton step + slow-path call) was a seventh of the sampler's instructions
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-2.0f * __logf(ua)));
   float sn, cs;
   __sincosf(ang, &sn, &cs);
   return make_float2(rad * cs, rad * sn);
