@@ -74,6 +74,7 @@ struct RefBase {
 };
 
 typedef NeuralNetModel<7, 2, 3, 6, 32, 32, 4> RefNN;
+typedef NeuralNetModel<7, 2, 3, 6, 64, 64, 64, 64, 4> RefNN64;  // SRC/params/models/wider_deeper_network_08_20_2020.npz
 typedef GeneralizedLinear<CarBasisFuncs, 7, 2, 25, CarKinematics, 3> RefBF;
 
 template <class MODEL, int ROLLOUTS, int BX, int BY>
@@ -206,21 +207,20 @@ struct RefImpl : RefBase {
   }
 };
 
-template <int ROLLOUTS, int BX, int BY>
-RefBase *make_nn(const float *theta, int negate_yaw, const float *lo_hi, const float *costmap, int w, int h,
+template <class NN, int NLAYERS, int ROLLOUTS, int BX, int BY>
+RefBase *make_nn_t(const int *widths, const float *theta, int negate_yaw, const float *lo_hi, const float *costmap, int w, int h,
                  const ref_cost_params *cp, const float *nu, const float *init_u, int hz, int T, int opt_stride, float gamma,
                  int num_iters, int *rc) {
-  auto *r = new RefImpl<RefNN, ROLLOUTS, BX, BY>();
+  auto *r = new RefImpl<NN, ROLLOUTS, BX, BY>();
   r->ranges[0] = make_float2(lo_hi[0], lo_hi[1]);
   r->ranges[1] = make_float2(lo_hi[2], lo_hi[3]);
-  r->model = new RefNN(1.0 / hz, r->ranges);  // SRC/path_integral_main.cu:100
+  r->model = new NN(1.0 / hz, r->ranges);  // SRC/path_integral_main.cu:100
   r->model->negate_yaw_der = negate_yaw != 0;
   // theta is packed [W1|b1|W2|b2|W3|b3] row-major (PI/neural_net_model.cu:125-141); hand it over through setParams
   typedef Eigen::Matrix<float, -1, -1, Eigen::RowMajor> RowMat;
-  const int widths[4] = {6, 32, 32, 4};
-  RowMat W[3], B[3];
+  RowMat W[NLAYERS - 1], B[NLAYERS - 1];
   size_t off = 0;
-  for (int l = 0; l < 3; l++) {
+  for (int l = 0; l < NLAYERS - 1; l++) {
     const int nin = widths[l], nout = widths[l + 1];
     W[l] = RowMat::Zero(nout, nin);
     B[l] = RowMat::Zero(nout, 1);
@@ -232,6 +232,22 @@ RefBase *make_nn(const float *theta, int negate_yaw, const float *lo_hi, const f
   r->model->setParams(W, B);
   *rc = r->init_common(lo_hi, costmap, w, h, cp, nu, init_u, hz, T, opt_stride, gamma, num_iters);
   return r;
+}
+
+template <int ROLLOUTS, int BX, int BY>
+RefBase *make_nn(const float *theta, int negate_yaw, const float *lo_hi, const float *costmap, int w, int h,
+                 const ref_cost_params *cp, const float *nu, const float *init_u, int hz, int T, int opt_stride, float gamma,
+                 int num_iters, int *rc) {
+  static const int widths[4] = {6, 32, 32, 4};
+  return make_nn_t<RefNN, 4, ROLLOUTS, BX, BY>(widths, theta, negate_yaw, lo_hi, costmap, w, h, cp, nu, init_u, hz, T, opt_stride, gamma, num_iters, rc);
+}
+
+template <int ROLLOUTS, int BX, int BY>
+RefBase *make_nn64(const float *theta, int negate_yaw, const float *lo_hi, const float *costmap, int w, int h,
+                   const ref_cost_params *cp, const float *nu, const float *init_u, int hz, int T, int opt_stride, float gamma,
+                   int num_iters, int *rc) {
+  static const int widths[6] = {6, 64, 64, 64, 64, 4};
+  return make_nn_t<RefNN64, 6, ROLLOUTS, BX, BY>(widths, theta, negate_yaw, lo_hi, costmap, w, h, cp, nu, init_u, hz, T, opt_stride, gamma, num_iters, rc);
 }
 
 template <int ROLLOUTS, int BX, int BY>
@@ -252,13 +268,14 @@ RefBase *make_bf(const float *theta, const float *lo_hi, const float *costmap, i
 
 extern "C" {
 
-enum { REF_NN_1920 = 0, REF_BF_2560 = 1, REF_NN_256 = 2, REF_NN_4096 = 3, REF_BF_256 = 4 };
+enum { REF_NN_1920 = 0, REF_BF_2560 = 1, REF_NN_256 = 2, REF_NN_4096 = 3, REF_BF_256 = 4, REF_NN64_1920 = 5 };
 
 const char *ref_version(void) { return "rdesc/autorally MPPIController (reference sources, sm_100a build, shimmed host libraries)"; }
 
 // kind: REF_NN_1920 = MPPIController<NeuralNetModel<7,2,3,6,32,32,4>, MPPICosts, 1920, 8, 16>  (SRC/path_integral_main.cu:66-69)
 //       REF_BF_2560 = MPPIController<GeneralizedLinear<CarBasisFuncs,7,2,25,CarKinematics,3>, MPPICosts, 2560, 16, 4>  (:71-74)
 //       REF_NN_256 / REF_NN_4096 / REF_BF_256 = the same controllers with 256 / 4096 rollouts (small fixtures, ragged sizes)
+//       REF_NN64_1920 = MPPIController<NeuralNetModel<7,2,3,6,64,64,64,64,4>, MPPICosts, 1920, 8, 16> (the fork's wider_deeper network)
 int ref_create(int kind, const float *theta, int negate_yaw, const float *lo_hi, const float *costmap, int w, int h,
                const ref_cost_params *cp, const float *nu, const float *init_u, int hz, int T, int opt_stride, float gamma,
                int num_iters, void **out) {
@@ -273,6 +290,7 @@ int ref_create(int kind, const float *theta, int negate_yaw, const float *lo_hi,
     case REF_NN_256: r = make_nn<256, 8, 16>(theta, negate_yaw, lo_hi, costmap, w, h, cp, nu, init_u, hz, T, opt_stride, gamma, num_iters, &rc); break;
     case REF_NN_4096: r = make_nn<4096, 8, 16>(theta, negate_yaw, lo_hi, costmap, w, h, cp, nu, init_u, hz, T, opt_stride, gamma, num_iters, &rc); break;
     case REF_BF_256: r = make_bf<256, 16, 4>(theta, lo_hi, costmap, w, h, cp, nu, init_u, hz, T, opt_stride, gamma, num_iters, &rc); break;
+    case REF_NN64_1920: r = make_nn64<1920, 8, 16>(theta, negate_yaw, lo_hi, costmap, w, h, cp, nu, init_u, hz, T, opt_stride, gamma, num_iters, &rc); break;
     default: return -1;
   }
   if (rc) { delete r; return rc; }

@@ -14,8 +14,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_ref", "libautorally_ref.so")
 
-REF_NN_1920, REF_BF_2560, REF_NN_256, REF_NN_4096, REF_BF_256 = 0, 1, 2, 3, 4
-KIND_ROLLOUTS = {REF_NN_1920: 1920, REF_BF_2560: 2560, REF_NN_256: 256, REF_NN_4096: 4096, REF_BF_256: 256}
+REF_NN_1920, REF_BF_2560, REF_NN_256, REF_NN_4096, REF_BF_256, REF_NN64_1920 = 0, 1, 2, 3, 4, 5
+KIND_ROLLOUTS = {REF_NN_1920: 1920, REF_BF_2560: 2560, REF_NN_256: 256, REF_NN_4096: 4096, REF_BF_256: 256, REF_NN64_1920: 1920}
 
 c_float_p = ctypes.POINTER(ctypes.c_float)
 _lib = None

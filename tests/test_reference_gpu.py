@@ -187,3 +187,25 @@ def test_randomized_scenarios_three_way(models, costmap, seed):
     compare(got, want, 100, "cuda vs reference (seed %d)" % seed)
     o = make_oracle("nn", models, costmap, cp).compute_control(state, U, HIST, NU, want["eps"], gamma=gamma, threads=8)
     compare(o, want, 100, "oracle vs reference (seed %d)" % seed)
+
+
+def test_wider_deeper_network_three_way(models, costmap):
+    """The fork's 6-64-64-64-64-4 network (SRC/params/models/wider_deeper_network_08_20_2020.npz) against the reference's own
+    MPPIController<NeuralNetModel<7,2,3,6,64,64,64,64,4>, MPPICosts, 1920, 8, 16> compiled from its sources: the tensor-core
+    kernel rollout_tc_kernel<64,4> (AUTO), the one-rollout-per-thread FP32 kernel, and the CPU oracle."""
+    cp = cost_params_for(costmap)
+    state, U = top_state(4.0), straight_controls(100)
+    theta = models["wider_deeper_theta"]
+    with ref.ReferenceController(ref.REF_NN64_1920, theta, costmap, cp, negate_yaw_der=False) as rc:
+        rc.set_controls(U, HIST)
+        want = rc.compute_control(state)
+        want["costs"], want["V"] = rc.rollout_costs(state, U, want["eps"][0])
+    for variant in (0, 1):
+        with make_context("nn", models, costmap, cp, 1920, tag="wider_deeper", negate_yaw_der=False, variant=variant) as ctx:
+            ctx.set_noise(want["eps"])
+            got = ctx.compute_control(state, U, HIST)
+            got["costs"], got["V"] = ctx.rollout_costs(), ctx.sampled_controls()
+            assert ctx.resolved_variant() == (10 if variant == 0 else 1)
+        compare(got, want, 100, "cuda (variant %d) vs reference, 64-wide network" % variant, cost_tol=3e-4)
+    o = make_oracle("nn", models, costmap, cp, tag="wider_deeper", negate_yaw_der=False).compute_control(state, U, HIST, NU, want["eps"], threads=8)
+    compare(o, want, 100, "oracle vs reference, 64-wide network", cost_tol=3e-4)
