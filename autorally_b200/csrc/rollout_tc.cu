@@ -56,14 +56,20 @@ constexpr float TANH_SCALE = 2.88539008177792681472f;  // 2 log2(e)
 
 // Geometry of one instantiation: 6 -> HID x NHID (tanh) -> 4.  NeuralNetModel<7,2,3,6,32,32,4> is <32, 2>, the
 // wider_deeper network 6-64-64-64-64-4 the fork ships (SRC/params/models/wider_deeper_network_08_20_2020.npz) <64, 4>.
-template <int HID, int NHID>
+template <int HID, int NHID, int TPC_ = 1>
 struct Geo {
   static_assert(HID == 32 || HID == 64, "hidden width 32 or 64");
   static_assert(NHID >= 2, "at least two hidden layers");
   static constexpr int NCH = HID / 16;                    // K = 16 chunks per hidden layer = 16-column epilogue chunks
   static constexpr int COL_D = 0;                         // accumulator, HID columns
   static constexpr int COL_A = HID;                       // activations: per chunk [hi(16 neurons) | lo(16 neurons)], 8 + 8 columns
-  static constexpr int TMEM_COLS = 2 * HID;               // power of two: 64 (8 CTAs per SM) or 128
+  static constexpr int TMEM_COLS = 2 * HID;               // per tile, power of two: 64 or 128
+  // Tiles (128-thread groups) per CTA.  The 56 KB of FP16 weights of the 64-wide network allow only 3 one-tile CTAs per SM;
+  // two tiles sharing one copy of the weights give 2 CTAs = 4 tiles per SM, all of the tensor memory (1 M rollouts: 14.4 ->
+  // 13.6 ms, 65536: 1.32 -> 1.06 ms).  Small problems keep one tile per CTA so that the tiles spread over more SMs (1920
+  // rollouts = 15 tiles: 0.54 ms on 15 SMs, 0.73 ms on 8).
+  static constexpr int TPC = TPC_;
+  static constexpr int THREADS = TILE * TPC;
   // shared-memory B matrices (FP16, canonical K-major no-swizzle: 8 rows x 16 bytes core matrices)
   static constexpr int SZ_B1 = HID * 16 * 2;              // N = HID, K = 16
   static constexpr int SZ_BH = HID * HID * 2;             // N = HID, K = HID
@@ -79,8 +85,8 @@ struct Geo {
   // file exactly, so a ninth CTA, which could only spin in tcgen05.alloc, never becomes resident); 3 at HID = 64 (56 KB of
   // weights each).  No shared-memory padding: padding the allocation to fence off extra CTAs costs L1 / texture cache
   // (unified with shared memory) and was measured 8 % slower at 1 M rollouts (profiles/exp_tc_cfg_r01.txt).  The launcher
-  // falls back to PAD_BYTES only if a build ever uses so few registers that one more CTA would fit.
-  static constexpr int MIN_CTAS = HID == 32 ? TC_MINCTAS : 3;
+  // falls back to padding only if a build ever uses so few registers that one more CTA would fit.
+  static constexpr int MIN_CTAS = HID == 32 ? TC_MINCTAS : (TPC == 2 ? 2 : 3);
   static constexpr int PAD_BYTES = (227 / MIN_CTAS - 2) * 1024;
   static constexpr int SMEM_BYTES = (TC_PAD && B_BYTES < PAD_BYTES) ? PAD_BYTES : B_BYTES;
   // packed transposed parameters: per layer Wt[k][j] then b[j]
@@ -238,55 +244,61 @@ __device__ __forceinline__ void put_split(unsigned char *hi_base, unsigned char 
   if (lo_base) *reinterpret_cast<__half *>(lo_base + b_off(N, n, k)) = l;
 }
 
-template <int HID, int NHID>
-__global__ void __launch_bounds__(TILE, Geo<HID, NHID>::MIN_CTAS)
+template <int HID, int NHID, int TPC>
+__global__ void __launch_bounds__(Geo<HID, NHID, TPC>::THREADS, Geo<HID, NHID, TPC>::MIN_CTAS)
 rollout_tc_kernel(const __grid_constant__ RolloutParams p, const __grid_constant__ TcEpilogue<HID, NHID> ep) {
-  using G = Geo<HID, NHID>;
+  using G = Geo<HID, NHID, TPC>;
   extern __shared__ __align__(1024) unsigned char smem[];
-  __shared__ __align__(8) unsigned long long mma_bar;
+  __shared__ __align__(8) unsigned long long mma_bar_sm[G::TPC];
   __shared__ uint32_t tmem_base_slot;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  // a CTA holds TPC independent tiles that share the weights in shared memory; `tid`, `warp` are relative to the tile
+  const int cta_tid = threadIdx.x, tile = cta_tid / TILE, tid = cta_tid - tile * TILE, warp = tid >> 5;
+  auto tile_sync = [&]() {  // barrier among the 128 threads of this tile (named barrier 1 + tile)
+    if (G::TPC == 1) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(1 + tile), "n"(TILE) : "memory");
+  };
 
   // ---- prologue: weights -> FP16 hi / lo B matrices in shared memory (theta_t: per layer Wt[k][j], then b[j]) ----
-  for (int i = tid; i < G::B_BYTES / 16; i += TILE) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = cta_tid; i < G::B_BYTES / 16; i += G::THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
   {
     const float *th = p.theta_t;
-    for (int i = tid; i < 6 * HID; i += TILE) {  // layer 1 weights, scaled
+    for (int i = cta_tid; i < 6 * HID; i += G::THREADS) {  // layer 1 weights, scaled
       const int k = i / HID, n = i - k * HID;
       const float w = __fmul_rn(th[G::TH_W1 + i], TANH_SCALE);
       put_split(smem + G::OFF_B1A, smem + G::OFF_B1B, HID, n, k, w);
       put_split(smem + G::OFF_B1A, nullptr, HID, n, 8 + k, w);
     }
-    for (int n = tid; n < HID; n += TILE)  // b1 rides in the K padding: the operand carries 1.0 at k = 6
+    for (int n = cta_tid; n < HID; n += G::THREADS)  // b1 rides in the K padding: the operand carries 1.0 at k = 6
       put_split(smem + G::OFF_B1A, smem + G::OFF_B1B, HID, n, 6, __fmul_rn(th[G::TH_B1 + n], TANH_SCALE));
 #pragma unroll
     for (int h = 1; h < NHID; h++) {  // hidden layer h acts on r of layer h - 1: -2 W (and the tanh scale)
       unsigned char *hi = smem + G::OFF_BH + (h - 1) * 2 * G::SZ_BH;
-      for (int i = tid; i < HID * HID; i += TILE) {
+      for (int i = cta_tid; i < HID * HID; i += G::THREADS) {
         const int k = i / HID, n = i - k * HID;
         put_split(hi, hi + G::SZ_BH, HID, n, k, __fmul_rn(th[G::th_w(h) + i], -2.0f * TANH_SCALE));
       }
     }
-    for (int i = tid; i < HID * 4; i += TILE) {  // output layer acts on r of the last hidden layer: -2 W (linear, no tanh scale)
+    for (int i = cta_tid; i < HID * 4; i += G::THREADS) {  // output layer acts on r of the last hidden layer: -2 W (linear, no tanh scale)
       const int k = i >> 2, n = i & 3;
       put_split(smem + G::OFF_BL, smem + G::OFF_BL + G::SZ_BL, 16, n, k, -2.0f * th[G::TH_WL + i]);
     }
   }
-  const uint32_t bar = smem_u32(&mma_bar);
+  const uint32_t bar = smem_u32(&mma_bar_sm[tile]);
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(G::TMEM_COLS) : "memory");
+  if (cta_tid < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(G::TMEM_COLS * G::TPC) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy weight stores -> visible to the tensor core
   fence_before();
   __syncthreads();
   fence_after();
-  const uint32_t tmem = tmem_base_slot;
+  const uint32_t tmem_cta = tmem_base_slot;
+  const uint32_t tmem = tmem_cta + (uint32_t)(tile * G::TMEM_COLS);  // this tile's columns
   const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);  // this warp's 32 TMEM lanes
 
   const uint32_t sb = (smem_u32(smem) & 0x3FFFFu) >> 4;
@@ -294,7 +306,7 @@ rollout_tc_kernel(const __grid_constant__ RolloutParams p, const __grid_constant
 
   // ---- rollout bookkeeping (rollout.cuh, R = 1) ----
   const long long total = (long long)p.B * p.n_local;
-  const long long g0 = (long long)blockIdx.x * TILE + tid;
+  const long long g0 = ((long long)blockIdx.x * G::TPC + tile) * TILE + tid;
   const bool valid = g0 < total;
   const long long gc = valid ? g0 : 0;  // idle threads shadow rollout 0 (they must take part in every barrier) and store nothing
   const int ctrl = (int)(gc / p.n_local);
@@ -353,7 +365,7 @@ rollout_tc_kernel(const __grid_constant__ RolloutParams p, const __grid_constant
     }
     wait_st();
     fence_before();
-    if (TC_EXP != 4) __syncthreads();
+    if (TC_EXP != 4) tile_sync();
     if (warp == 0 && TC_EXP != 3 && TC_EXP != 4) {
       if (tid == 0) {
         fence_after();
@@ -392,7 +404,7 @@ rollout_tc_kernel(const __grid_constant__ RolloutParams p, const __grid_constant
       }
       wait_st();
       fence_before();
-      if (TC_EXP != 4) __syncthreads();
+      if (TC_EXP != 4) tile_sync();
       if (warp == 0 && TC_EXP != 3 && TC_EXP != 4) {
         if (tid == 0) {
           fence_after();
@@ -461,16 +473,16 @@ rollout_tc_kernel(const __grid_constant__ RolloutParams p, const __grid_constant
   if ((tid & 31) == 0 && wbest != 0xffffffffu) atomicMin(p.baseline + wctrl, wbest);
   fence_before();
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(G::TMEM_COLS) : "memory");
+  if (cta_tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_cta), "r"(G::TMEM_COLS * G::TPC) : "memory");
 }
 
 }  // namespace tc
 
-template <int HID, int NHID>
+template <int HID, int NHID, int TPC>
 static cudaError_t launch_tc(const RolloutParams &p, cudaStream_t st, const float *host_theta_t) {
-  using G = tc::Geo<HID, NHID>;
+  using G = tc::Geo<HID, NHID, TPC>;
   const long long total = (long long)p.B * p.n_local;
-  const unsigned grid = (unsigned)((total + tc::TILE - 1) / tc::TILE);
+  const unsigned grid = (unsigned)((total + G::THREADS - 1) / G::THREADS);
   // the folded biases are b + rowsum(W) (tanh = 1 - 2r travels as r); theta_t holds Wt[k][j] per layer, then b[j]
   tc::TcEpilogue<HID, NHID> ep;
   for (int j = 0; j < HID; j++) ep.eb[0][j] = 1.0f;  // unused: the first layer's bias rides in the K padding of its MMA
@@ -488,25 +500,29 @@ static cudaError_t launch_tc(const RolloutParams &p, cudaStream_t st, const floa
   static int smem_bytes = 0;  // decided once per instantiation
   if (smem_bytes == 0) {
     cudaFuncAttributes fa;
-    cudaError_t e = cudaFuncGetAttributes(&fa, tc::rollout_tc_kernel<HID, NHID>);
+    cudaError_t e = cudaFuncGetAttributes(&fa, tc::rollout_tc_kernel<HID, NHID, TPC>);
     if (e != cudaSuccess) return e;
     int bytes = G::SMEM_BYTES;
-    const long long tmem_tiles = 512 / G::TMEM_COLS;
-    const bool regs_admit_more = (long long)fa.numRegs * tc::TILE * (tmem_tiles + 1) <= 65536;
-    const bool smem_admits_more = (long long)(bytes + 2048) * (tmem_tiles + 1) <= 228 * 1024;
-    if (regs_admit_more && smem_admits_more) bytes = ((228 / (int)(tmem_tiles + 1)) - 1) * 1024;  // keep TMEM the only limiter
+    const long long tmem_ctas = 512 / (G::TMEM_COLS * G::TPC);  // CTAs per SM the tensor memory admits
+    const bool regs_admit_more = (long long)fa.numRegs * G::THREADS * (tmem_ctas + 1) <= 65536;
+    const bool smem_admits_more = (long long)(bytes + 2048) * (tmem_ctas + 1) <= 228 * 1024;
+    if (regs_admit_more && smem_admits_more) bytes = ((228 / (int)(tmem_ctas + 1)) - 1) * 1024;  // keep TMEM the only limiter
     if (bytes > 48 * 1024) {
-      e = cudaFuncSetAttribute(tc::rollout_tc_kernel<HID, NHID>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+      e = cudaFuncSetAttribute(tc::rollout_tc_kernel<HID, NHID, TPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
       if (e != cudaSuccess) return e;
     }
     smem_bytes = bytes;
   }
-  tc::rollout_tc_kernel<HID, NHID><<<grid, tc::TILE, smem_bytes, st>>>(p, ep);
+  tc::rollout_tc_kernel<HID, NHID, TPC><<<grid, G::THREADS, smem_bytes, st>>>(p, ep);
   return cudaGetLastError();
 }
 
-cudaError_t launch_rollout_nn32_tc(const RolloutParams &p, cudaStream_t st, const float *host_theta_t) { return launch_tc<32, 2>(p, st, host_theta_t); }
-cudaError_t launch_rollout_nn64_tc(const RolloutParams &p, cudaStream_t st, const float *host_theta_t) { return launch_tc<64, 4>(p, st, host_theta_t); }
+cudaError_t launch_rollout_nn32_tc(const RolloutParams &p, cudaStream_t st, const float *host_theta_t) { return launch_tc<32, 2, 1>(p, st, host_theta_t); }
+cudaError_t launch_rollout_nn64_tc(const RolloutParams &p, cudaStream_t st, const float *host_theta_t) {
+  // up to two one-tile CTAs per SM: spread the tiles; beyond that, two tiles per CTA share the weights (4 tiles per SM)
+  const long long tiles = ((long long)p.B * p.n_local + tc::TILE - 1) / tc::TILE;
+  return tiles <= 2 * 148 ? launch_tc<64, 4, 1>(p, st, host_theta_t) : launch_tc<64, 4, 2>(p, st, host_theta_t);
+}
 
 // True when every folded bias of the network keeps e^(2 b) inside the FP32 range (|b| < 40); otherwise the caller uses
 // the FP32 kernels.  widths = {6, HID x NHID, 4}.

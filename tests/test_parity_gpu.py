@@ -357,3 +357,26 @@ def test_tensor_kernel_declines_networks_whose_folded_biases_leave_fp32_range(mo
         assert ctx.resolved_variant() == 2
         out = ctx.compute_control(top_state(4.0), straight_controls(100))
         assert np.isfinite(out["U"]).all()
+
+
+def test_wider_deeper_65536_two_tile_ctas_agree_with_fp32_kernel(models, costmap):
+    """Above 37888 rollouts the 64-wide tensor-core kernel runs two tiles per CTA (shared weights, named barriers, one tensor
+    memory allocation split in two): same Philox noise through it and through the one-rollout-per-thread FP32 kernel."""
+    cp = cost_params_for(costmap)
+    N, T = 65536, 100
+    state, U = top_state(4.0), straight_controls(T)
+    res = {}
+    for variant in (0, 1):
+        with make_context("nn", models, costmap, cp, N, tag="wider_deeper", negate_yaw_der=False, variant=variant) as ctx:
+            ctx.use_sampler()
+            ctx.seed(4321, 0)
+            out = ctx.compute_control(state, U)
+            out["costs"], out["crash"] = ctx.rollout_costs(), ctx.rollout_crash()
+            assert ctx.resolved_variant() == (10 if variant == 0 else 1)
+            res[variant] = out
+    a, b = res[0], res[1]
+    assert (a["crash"] == b["crash"]).mean() > 0.998
+    check_costs(a["costs"], b["costs"], T, cost_tol=3e-4, min_ok=0.99)
+    assert abs(a["baseline"] - b["baseline"]) <= 3e-4 * (1 + abs(b["baseline"]))
+    assert rel_err(a["U"], b["U"]).max() < 3e-4
+    assert rel_err(a["state_solution"], b["state_solution"]).max() < 1e-4
