@@ -18,7 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libmppi_b200.so")
 
 MPPI_DYNAMICS_NN, MPPI_DYNAMICS_BF = 0, 1
-ROLLOUT_AUTO, ROLLOUT_THREAD1, ROLLOUT_THREAD2, ROLLOUT_SPLIT8, ROLLOUT_CONST1 = 0, 1, 2, 3, 4
+ROLLOUT_AUTO, ROLLOUT_THREAD1, ROLLOUT_THREAD2, ROLLOUT_HALF16, ROLLOUT_TENSOR, ROLLOUT_GENERIC = 0, 1, 2, 9, 10, 11
 MPPI_ERR_NO_DEVICE = -4
 
 c_float_p = ctypes.POINTER(ctypes.c_float)
@@ -37,7 +37,7 @@ EXPORTED_SYMBOLS = [
     "mppi_shard_begin_async", "mppi_shard_finish_async", "mppi_shard_result", "mppi_set_stream",
     "mppi_comm_unique_id", "mppi_comm_init", "mppi_comm_destroy", "mppi_compute_control_sharded",
     "mppi_run_resident_sharded", "mppi_compute_control_async", "mppi_compute_control_wait",
-    "mppi_bench_compute_control", "mppi_p2p_export", "mppi_p2p_init", "mppi_p2p_destroy",
+    "mppi_bench_compute_control", "mppi_p2p_export", "mppi_p2p_init", "mppi_p2p_destroy", "mppi_set_fused_noise",
 ]
 
 
@@ -46,7 +46,8 @@ class MppiConfig(ctypes.Structure):
                 ("num_controllers", ctypes.c_int), ("rollout_begin", ctypes.c_int), ("rollout_count", ctypes.c_int),
                 ("hz", ctypes.c_int), ("optimization_stride", ctypes.c_int), ("gamma", ctypes.c_float),
                 ("num_iters", ctypes.c_int), ("bdim_x", ctypes.c_int), ("bdim_y", ctypes.c_int),
-                ("device", ctypes.c_int), ("rollout_variant", ctypes.c_int), ("seed", ctypes.c_uint64)]
+                ("device", ctypes.c_int), ("rollout_variant", ctypes.c_int), ("controller_begin", ctypes.c_int),
+                ("seed", ctypes.c_uint64)]
 
 
 class MppiResult(ctypes.Structure):
@@ -100,7 +101,7 @@ class MppiContext:
 
     def __init__(self, dynamics="nn", num_rollouts=1920, num_timesteps=100, num_controllers=1, rollout_begin=0,
                  rollout_count=0, hz=50, optimization_stride=1, gamma=0.15, num_iters=1, bdim=(8, 16), device=-1,
-                 variant=ROLLOUT_AUTO, seed=1234):
+                 variant=ROLLOUT_AUTO, seed=1234, controller_begin=0):
         self.lib = load_library()
         cfg = MppiConfig()
         self.lib.mppi_config_default(ctypes.byref(cfg))
@@ -109,6 +110,7 @@ class MppiContext:
         cfg.rollout_begin, cfg.rollout_count = rollout_begin, rollout_count
         cfg.hz, cfg.optimization_stride, cfg.gamma, cfg.num_iters = hz, optimization_stride, gamma, num_iters
         cfg.bdim_x, cfg.bdim_y, cfg.device, cfg.rollout_variant, cfg.seed = bdim[0], bdim[1], device, variant, seed
+        cfg.controller_begin = controller_begin
         self.cfg = cfg
         self.B, self.T = num_controllers, num_timesteps
         self.n_local = rollout_count if rollout_count else num_rollouts - rollout_begin
@@ -180,6 +182,10 @@ class MppiContext:
 
     def seed(self, seed, call_counter=0):
         self._ck(self.lib.mppi_seed(self._ctx, seed, call_counter), "mppi_seed")
+
+    def set_fused_noise(self, mode):
+        """1: the rollout kernel draws its own Philox noise, 0: stand-alone sampler kernel, -1: automatic."""
+        self._ck(self.lib.mppi_set_fused_noise(self._ctx, int(mode)), "mppi_set_fused_noise")
 
     def sample_noise(self):
         eps = np.zeros((self.B, self.n_local, self.T, 2), np.float32)

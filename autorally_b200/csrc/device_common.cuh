@@ -36,6 +36,12 @@ struct RolloutParams {
   int negate_yaw;
   DevCostParams cp;
   cudaTextureObject_t tex;
+  // Noise generated in place (philox.cuh): fused_noise != 0 -> the kernel draws eps[r][t][:] itself from the Philox stream
+  // (same counters as sample_noise_kernel, bit-identical values) instead of reading it from `du`; `du` then only receives
+  // the sampled controls.  call_ptr is the device-resident compute-call counter finalize_kernel advances.
+  int fused_noise, b_begin;
+  uint32_t seed_lo, seed_hi;
+  const uint32_t *call_ptr;
 };
 
 constexpr int INBOX_STATE = 0;

@@ -55,7 +55,7 @@ struct mppi_ctx {
   const float *p2p_mailbox_half() const { return p2p_mailbox + (size_t)(p2p_seq & 1u) * p2p_size * B * shard_floats; }
   // model
   bool have_model = false, have_cost_params = false, have_map = false, have_inbox = false;
-  int net_kind = 0;  // 0 none, 32 = 6-32-32-4, 64 = 6-64-64-64-64-4
+  int net_kind = 0;  // 0 none, 32 = 6-32-32-4, 64 = 6-64-64-64-64-4, 1 = any other layer pack (run-time layer kernels)
   std::vector<int> net_structure;
   std::vector<float> theta_t;
   float *d_theta_t = nullptr;
@@ -92,6 +92,7 @@ struct mppi_ctx {
   std::vector<float> injected_noise;
   uint64_t seed = 1234;
   uint32_t *d_call_counter = nullptr;
+  int fused_mode = -1;  // mppi_set_fused_noise: -1 automatic, 0 sampler kernel, 1 in the rollout kernel
   // CUDA graph of one complete computeControl (H2D inbox -> kernels -> D2H outbox)
   cudaGraphExec_t graph_exec = nullptr;
   bool graph_valid = false;
@@ -136,6 +137,8 @@ int resolve_variant(const mppi_ctx *c) {
   int v = c->cfg.rollout_variant;
   const long long total = (long long)c->B * c->n_local;
   if (c->cfg.dynamics == MPPI_DYNAMICS_BF) return MPPI_ROLLOUT_THREAD1;
+  // a layer pack without a dedicated kernel; selectable for the two shipped networks as well (tests)
+  if (c->net_kind == 1 || v == MPPI_ROLLOUT_GENERIC) return MPPI_ROLLOUT_GENERIC;
   if (c->net_kind == 64) {
     // 6-64-64-64-64-4: the tensor-core kernel at every size (1920 x 100: 5.4 ms -> see profiles/exp_tc64_r01.txt); the
     // one-rollout-per-thread FP32 kernel stays selectable and is the fallback for out-of-range biases
@@ -153,7 +156,7 @@ int resolve_variant(const mppi_ctx *c) {
   // the tensor-core kernel folds the hidden-layer biases into its exponentials as e^(2 b1) and e^(2 (b2 + rowsum W2))
   // (rollout_tc.cu): beyond +-40 these would leave the FP32 range, so such a network runs on the FFMA2 kernel instead
   if (v == MPPI_ROLLOUT_TENSOR && !(c->theta_t.size() >= 1412 && tc_biases_in_range(c->theta_t.data(), 32, 2))) v = MPPI_ROLLOUT_THREAD2;
-  if (v == MPPI_ROLLOUT_CONST1) v = MPPI_ROLLOUT_THREAD2;  // constant-bank weights measured no faster (profiles/microbench_r01.txt)
+  if (v != MPPI_ROLLOUT_THREAD1 && v != MPPI_ROLLOUT_THREAD2 && v != MPPI_ROLLOUT_HALF16 && v != MPPI_ROLLOUT_TENSOR) v = MPPI_ROLLOUT_THREAD1;
   return v;
 }
 
@@ -168,6 +171,18 @@ cudaError_t launch_pdl(mppi_ctx *c, K kernel, dim3 grid, int block, size_t smem,
   return cudaLaunchKernelEx(&cfg, kernel, params);
 }
 
+// Can this context's rollout kernel draw its Philox noise in place?  The half-warp and two-warp latency kernels and the
+// FFMA2 kernel (register-bound) read the buffer the sampler kernel fills.
+bool supports_fused_noise(const mppi_ctx *c) {
+  const long long total = (long long)c->B * c->n_local;
+  if (c->cfg.dynamics == MPPI_DYNAMICS_BF) return !rollout_bf_is_split(total);
+  return c->variant == MPPI_ROLLOUT_TENSOR || c->variant == MPPI_ROLLOUT_THREAD1 || c->variant == MPPI_ROLLOUT_GENERIC;
+}
+bool fused_noise_now(const mppi_ctx *c) {
+  if (c->injected || c->fused_mode == 0 || !supports_fused_noise(c)) return false;
+  return true;  // automatic = in place wherever the kernel supports it (no sampler launch, no noise round trip through HBM)
+}
+
 cudaError_t launch_rollout(mppi_ctx *c) {
   RolloutParams p{};
   p.inbox = c->d_inbox; p.du = c->d_du; p.costs = c->d_costs; p.crash = c->d_crash; p.baseline = c->d_baseline;
@@ -178,18 +193,17 @@ cudaError_t launch_rollout(mppi_ctx *c) {
   p.lo0 = c->ranges[0]; p.hi0 = c->ranges[1]; p.lo1 = c->ranges[2]; p.hi1 = c->ranges[3];
   p.dt = c->dt; p.negate_yaw = (c->cfg.dynamics == MPPI_DYNAMICS_BF) ? 1 : c->negate_yaw;
   p.cp = c->dev_cp; p.tex = c->map_tex;
+  p.fused_noise = fused_noise_now(c) ? 1 : 0; p.b_begin = c->cfg.controller_begin;
+  p.seed_lo = (uint32_t)c->seed; p.seed_hi = (uint32_t)(c->seed >> 32); p.call_ptr = c->d_call_counter;
   const long long total = (long long)c->B * c->n_local;
   const bool small = total <= 148LL * 4 * 32 * 4;
   c->launches++;
   if (c->cfg.dynamics == MPPI_DYNAMICS_BF) return launch_rollout_bf(p, c->stream, small);
+  if (c->variant == MPPI_ROLLOUT_GENERIC) return launch_rollout_generic(p, c->stream, c->net_structure.data(), (int)c->net_structure.size());
   if (c->net_kind == 64)
     return c->variant == MPPI_ROLLOUT_TENSOR ? launch_rollout_nn64_tc(p, c->stream, c->theta_t.data()) : launch_rollout_nn64_r1(p, c->stream, small);
   switch (c->variant) {
     case MPPI_ROLLOUT_THREAD2: return launch_rollout_nn32_r2(p, c->stream, small);
-    case MPPI_ROLLOUT_SPLIT8: return launch_rollout_nn32_split8(p, c->stream);
-    case MPPI_ROLLOUT_LANES8: return launch_rollout_nn32_lanes(p, c->stream, 8);
-    case MPPI_ROLLOUT_LANES16: return launch_rollout_nn32_lanes(p, c->stream, 16);
-    case MPPI_ROLLOUT_LANES32: return launch_rollout_nn32_lanes(p, c->stream, 32);
     case MPPI_ROLLOUT_TENSOR: return launch_rollout_nn32_tc(p, c->stream, c->theta_t.data());
     case MPPI_ROLLOUT_HALF16: return launch_rollout_nn32_half(p, c->stream, c->pdl && !c->injected);
     default: return launch_rollout_nn32_r1(p, c->stream, small);
@@ -202,7 +216,7 @@ cudaError_t launch_noise(mppi_ctx *c, bool pull_inbox = false) {
   if (blocks > 148 * 16) blocks = 148 * 16;
   c->launches++;
   sample_noise_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(
-      c->d_du, c->n_local, c->r_begin, c->T, c->B, (uint32_t)c->seed, (uint32_t)(c->seed >> 32), c->d_call_counter,
+      c->d_du, c->n_local, c->r_begin, c->T, c->B, c->cfg.controller_begin, (uint32_t)c->seed, (uint32_t)(c->seed >> 32), c->d_call_counter,
       pull_inbox ? reinterpret_cast<const float4 *>(c->h_inbox_dev) : nullptr, reinterpret_cast<float4 *>(c->d_inbox),
       c->B * c->inbox_stride / 4, FastDiv::make((uint32_t)((c->T + 1) / 2)), FastDiv::make((uint32_t)c->n_local));
   return cudaGetLastError();
@@ -277,8 +291,11 @@ int run_front(mppi_ctx *c, int iter, bool pull_inbox = false) {
     const size_t per_iter = (size_t)c->B * c->n_local * c->T * 2;
     if (c->injected_noise.size() < per_iter * (size_t)(iter + 1)) return MPPI_ERR_INVALID_ARG;
     CK(cudaMemcpyAsync(c->d_du, c->injected_noise.data() + per_iter * iter, per_iter * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-  } else {
+  } else if (!fused_noise_now(c)) {
     CK(launch_noise(c, pull_inbox));
+  } else if (pull_inbox) {
+    // no sampler launch to piggy-back the zero-copy inbox pull on: an explicit copy node instead
+    CK(cudaMemcpyAsync(c->d_inbox, c->h_inbox, (size_t)c->B * c->inbox_stride * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   }
   CK(launch_rollout(c));   // the baseline slots were re-armed by the previous finalize_kernel
   CK(launch_weighting(c));
@@ -451,10 +468,18 @@ int mppi_set_nn_params(mppi_ctx *c, const float *theta, const int *net_structure
   if (!c || !theta || !net_structure || num_layers < 2 || num_layers > 16) return MPPI_ERR_INVALID_ARG;
   if (c->cfg.dynamics != MPPI_DYNAMICS_NN) return MPPI_ERR_INVALID_ARG;
   static const int s32[] = {6, 32, 32, 4}, s64[] = {6, 64, 64, 64, 64, 4};
-  int kind = 0;
+  // NeuralNetModel<7,2,3, layers...>: the network maps [roll, u_x, u_y, yaw rate, steering, throttle] to four derivatives
+  // (PI/neural_net_model.cu:372-377,406-409); any layer pack in between runs on the run-time layer kernels (widths <= 128)
+  if (net_structure[0] != 6 || net_structure[num_layers - 1] != 4) return MPPI_ERR_INVALID_ARG;
+  size_t nparams = 0;
+  for (int l = 0; l < num_layers; l++) {
+    if (net_structure[l] < 1 || net_structure[l] > 128) return MPPI_ERR_UNSUPPORTED;
+    if (l + 1 < num_layers) nparams += (size_t)(net_structure[l] + 1) * net_structure[l + 1];
+  }
+  if (nparams > 40000) return MPPI_ERR_UNSUPPORTED;  // finalize_kernel stages the parameters in shared memory
+  int kind = 1;  // 1 = run-time layer pack (rollout_generic_kernel, finalize_kernel<0>)
   if (num_layers == 4 && !std::memcmp(net_structure, s32, sizeof(s32))) kind = 32;
   if (num_layers == 6 && !std::memcmp(net_structure, s64, sizeof(s64))) kind = 64;
-  if (!kind) return MPPI_ERR_UNSUPPORTED;  // kernels are instantiated for the two shipped shapes
   c->net_kind = kind;
   c->net_structure.assign(net_structure, net_structure + num_layers);
   // [W1|b1|W2|b2|...] row-major (PI/neural_net_model.cu:125-141) -> per layer Wt[k][j] then b[j]
@@ -580,6 +605,14 @@ int mppi_seed(mppi_ctx *c, uint64_t seed, uint32_t call_counter) {
   CK(cudaSetDevice(c->device));
   CK(cudaStreamSynchronize(c->stream));
   CK(cudaMemcpy(c->d_call_counter, &call_counter, sizeof(uint32_t), cudaMemcpyHostToDevice));
+  return MPPI_OK;
+}
+
+int mppi_set_fused_noise(mppi_ctx *c, int mode) {
+  if (!c || mode < -1 || mode > 1) return MPPI_ERR_INVALID_ARG;
+  if (c->fused_mode == mode) return MPPI_OK;
+  c->fused_mode = mode;
+  c->graph_valid = false;
   return MPPI_OK;
 }
 
@@ -1005,7 +1038,7 @@ int mppi_run_resident(mppi_ctx *c, int steps, int flush_l2, float *elapsed_ms, f
     if (flush_l2) CK(cudaMemsetAsync(c->d_flush, s & 0xff, kFlushBytes, c->stream));
     if (per_step) CK(cudaEventRecord(c->step_events[4 * s], c->stream));
     for (int it = 0; it < c->cfg.num_iters; it++) {
-      CK(launch_noise(c));
+      if (!fused_noise_now(c)) CK(launch_noise(c));
       // events inside the pipeline serialise it (no programmatic overlap): only when the kernel time is asked for
       if (rollout_kernel_ms && it == 0) CK(cudaEventRecord(c->step_events[4 * s + 2], c->stream));
       CK(launch_rollout(c));

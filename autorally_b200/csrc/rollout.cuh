@@ -5,6 +5,7 @@
 #pragma once
 #include "device_common.cuh"
 #include "dynamics.cuh"
+#include "philox.cuh"
 
 namespace mppi {
 
@@ -109,7 +110,8 @@ __device__ __forceinline__ float running_cost_step(const DevCostParams &cp, cuda
 
 // One thread owns DYN::R consecutive rollouts.  Grid covers B * n_local rollouts; n_local is a
 // multiple of 64, so a warp never straddles two controllers and is either fully valid or idle.
-template <class DYN, int BLOCK, int MINB = 1>
+// FUSED: the noise is drawn in place from the Philox stream (philox.cuh) instead of being read from `du`.
+template <class DYN, int BLOCK, int MINB = 1, bool FUSED = false>
 __global__ void __launch_bounds__(BLOCK, MINB) rollout_kernel(const __grid_constant__ RolloutParams p) {
   constexpr int R = DYN::R;
   extern __shared__ float4 smem4[];
@@ -134,6 +136,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) rollout_kernel(const __grid_const
     int crash[R];
     bool noise_free[R], pure_noise[R];
     float2 *row[R];
+    FusedNoise fz[R];
+    const uint32_t call = FUSED ? *p.call_ptr : 0u;
 #pragma unroll
     for (int r = 0; r < R; r++) {
 #pragma unroll
@@ -144,6 +148,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) rollout_kernel(const __grid_const
       noise_free[r] = (rg == 0);
       pure_noise[r] = (rg >= p.pure_noise_from);
       row[r] = reinterpret_cast<float2 *>(p.du) + (size_t)(g0 + r) * p.T;
+      fz[r].r_global = (uint32_t)rg; fz[r].b_global = (uint32_t)(p.b_begin + ctrl); fz[r].call = call;
+      fz[r].seed_lo = p.seed_lo; fz[r].seed_hi = p.seed_hi; fz[r].held = make_float2(0.0f, 0.0f);
     }
     // one rollout per thread (the latency-bound shapes: basis functions, 64-wide FP32 kernel): fetch the costmap texels a
     // step ahead; the two-rollouts-per-thread FFMA2 kernel is register-bound and keeps the plain order
@@ -153,7 +159,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) rollout_kernel(const __grid_const
     for (int r = 0; r < R; r++) { front[r] = 0.0f; back[r] = 0.0f; }
     float2 e_next[R];
 #pragma unroll
-    for (int r = 0; r < R; r++) e_next[r] = EARLY_TEXELS ? row[r][0] : make_float2(0.0f, 0.0f);
+    for (int r = 0; r < R; r++) e_next[r] = (EARLY_TEXELS && !FUSED) ? row[r][0] : make_float2(0.0f, 0.0f);
     for (int i = 0; i < p.T; i++) {
       const float2 Ui = U[i];
       float in[6][R];
@@ -162,7 +168,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) rollout_kernel(const __grid_const
       for (int r = 0; r < R; r++) {
         // PI/mppi_controller.cu:130-155
         float2 e;
-        if (EARLY_TEXELS) {  // one rollout per thread: the noise of the next step is requested a step ahead as well
+        if (FUSED) {
+          e = fz[r].step(i);
+        } else if (EARLY_TEXELS) {  // one rollout per thread: the noise of the next step is requested a step ahead as well
           e = e_next[r];
           if (i + 1 < p.T) e_next[r] = row[r][i + 1];
         } else {

@@ -133,16 +133,22 @@ __global__ void __launch_bounds__(64) rollout_bf_split_kernel(const __grid_const
 
 }  // namespace
 
+// true when launch_rollout_bf would pick the two-warp latency kernel (which reads its noise from the buffer in both warps)
+bool rollout_bf_is_split(long long total) {
+  static const char *force = std::getenv("MPPI_BF_SPLIT");
+  return force ? std::atoi(force) != 0 : total <= 148LL * 32 * 4;
+}
+
 cudaError_t launch_rollout_bf(const RolloutParams &p, cudaStream_t st, bool small) {
   const long long total = (long long)p.B * p.n_local;
   // latency regime (under four 32-rollout CTAs per SM): the two-warp split; MPPI_BF_SPLIT=0/1 forces either kernel
   static const char *force = std::getenv("MPPI_BF_SPLIT");
-  const bool split = force ? std::atoi(force) != 0 : total <= 148LL * 32 * 4;
+  const bool split = !p.fused_noise && (force ? std::atoi(force) != 0 : total <= 148LL * 32 * 4);
   if (split) {
     rollout_bf_split_kernel<<<(unsigned)(total / 32), 64, 0, st>>>(p);
     return cudaGetLastError();
   }
-  return small ? launch_rollout_t<CarBasisDyn, 32>(p, st) : launch_rollout_t<CarBasisDyn, 128>(p, st);
+  return small ? launch_rollout_t<CarBasisDyn, 32, 1, true>(p, st) : launch_rollout_t<CarBasisDyn, 128, 1, true>(p, st);
 }
 
 }  // namespace mppi

@@ -13,7 +13,7 @@
 //  * per block of 16 timesteps, lane l prepares timestep i0 + l in parallel (noise, perturbation, un-clamped
 //    write-back, clamp; PI/mppi_controller.cu:130-159) and evaluates its running cost afterwards in parallel
 //    (positions by a sequential FMA prefix, sincosf, costmap fetches, PI/costs.cu:307-393; sticky crash flag as a
-//    prefix-OR over ballots), exactly as rollout_lanes.cu does;
+//    prefix-OR over ballots);
 //  * the step costs go to shared memory and the running mean (float difference, double update,
 //    PI/mppi_controller.cu:162-165) is replayed once, in order, at the end: its double-precision dependent chain
 //    stalled the in-order pipeline when interleaved with the recursion (14% of the stall samples).

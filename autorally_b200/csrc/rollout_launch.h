@@ -8,8 +8,6 @@ namespace mppi {
 // `small` selects 32-thread CTAs so that a few thousand rollouts still spread over many SMs.
 cudaError_t launch_rollout_nn32_r1(const RolloutParams &p, cudaStream_t st, bool small);
 cudaError_t launch_rollout_nn32_r2(const RolloutParams &p, cudaStream_t st, bool small);
-cudaError_t launch_rollout_nn32_split8(const RolloutParams &p, cudaStream_t st);
-cudaError_t launch_rollout_nn32_lanes(const RolloutParams &p, cudaStream_t st, int lanes);
 // pdl: launch with programmatic stream serialization (the kernel overlaps its prologue with its predecessor's tail)
 cudaError_t launch_rollout_nn32_half(const RolloutParams &p, cudaStream_t st, bool pdl);
 // tcgen05 tensor-core MLP (FP16 hi/lo split, activations in tensor memory): the filled-GPU kernel
@@ -18,5 +16,8 @@ cudaError_t launch_rollout_nn64_tc(const RolloutParams &p, cudaStream_t st, cons
 bool tc_biases_in_range(const float *host_theta_t, int hid, int nhid);
 cudaError_t launch_rollout_nn64_r1(const RolloutParams &p, cudaStream_t st, bool small);
 cudaError_t launch_rollout_bf(const RolloutParams &p, cudaStream_t st, bool small);
+bool rollout_bf_is_split(long long total);
+// run-time layer pack (any NeuralNetModel<7,2,3,6,...,4> with widths <= 128): rollout_generic.cu
+cudaError_t launch_rollout_generic(const RolloutParams &p, cudaStream_t st, const int *net_structure, int num_layers);
 
 }  // namespace mppi

@@ -4,6 +4,6 @@ namespace mppi {
 cudaError_t launch_rollout_nn64_r1(const RolloutParams &p, cudaStream_t st, bool small) {
   using D = NeuralNetDyn<1, 6, 64, 64, 64, 64, 4>;
   (void)small;
-  return launch_rollout_t<D, 64>(p, st);
+  return launch_rollout_t<D, 64, 1, true>(p, st);
 }
 }  // namespace mppi

@@ -244,7 +244,9 @@ __device__ __forceinline__ void put_split(unsigned char *hi_base, unsigned char 
   if (lo_base) *reinterpret_cast<__half *>(lo_base + b_off(N, n, k)) = l;
 }
 
-template <int HID, int NHID, int TPC>
+// FUSED: the noise of a timestep pair is drawn in place from the Philox stream (philox.cuh) inside the wait for the output
+// layer's MMAs instead of being read from `du` (800-byte stride, written by a separate sampler launch).
+template <int HID, int NHID, int TPC, bool FUSED>
 __global__ void __launch_bounds__(Geo<HID, NHID, TPC>::THREADS, Geo<HID, NHID, TPC>::MIN_CTAS)
 rollout_tc_kernel(const __grid_constant__ RolloutParams p, const __grid_constant__ TcEpilogue<HID, NHID> ep) {
   using G = Geo<HID, NHID, TPC>;
@@ -327,13 +329,21 @@ rollout_tc_kernel(const __grid_constant__ RolloutParams p, const __grid_constant
   // The controls of a step do not depend on the state, so they are prepared one step ahead, inside the wait for the last
   // layer of the previous step (PI/mppi_controller.cu:130-155 + enforceConstraints).  The noise row has an 800-byte
   // stride (every fetch is its own DRAM sector) and is requested a whole step before it is used.
-  float2 e_next = row[0];
+  float2 e_next = FUSED ? make_float2(0.0f, 0.0f) : row[0];
+  FusedNoise fz;
+  fz.r_global = (uint32_t)rg; fz.b_global = (uint32_t)(p.b_begin + ctrl); fz.call = FUSED ? *p.call_ptr : 0u;
+  fz.seed_lo = p.seed_lo; fz.seed_hi = p.seed_hi; fz.held = make_float2(0.0f, 0.0f);
   float control_cost;    // control cost of the prepared step (PI/costs.cu:307-313): a function of the controls only
   uint32_t ua_hi, ua_lo;  // FP16 hi / lo pairs of the clamped controls, ready for the layer-1 operand
   auto prepare_controls = [&](int i) {
     const float2 Ui = U[i];
-    const float2 e = e_next;
-    if (i + 1 < p.T) e_next = row[i + 1];
+    float2 e;
+    if (FUSED) {
+      e = fz.step(i);
+    } else {
+      e = e_next;
+      if (i + 1 < p.T) e_next = row[i + 1];
+    }
     float du0, du1, u0, u1;
     if (noise_free || i < p.opt_delay) {
       du0 = 0.0f; du1 = 0.0f; u0 = Ui.x; u1 = Ui.y;
@@ -478,8 +488,8 @@ rollout_tc_kernel(const __grid_constant__ RolloutParams p, const __grid_constant
 
 }  // namespace tc
 
-template <int HID, int NHID, int TPC>
-static cudaError_t launch_tc(const RolloutParams &p, cudaStream_t st, const float *host_theta_t) {
+template <int HID, int NHID, int TPC, bool FUSED>
+static cudaError_t launch_tc_f(const RolloutParams &p, cudaStream_t st, const float *host_theta_t) {
   using G = tc::Geo<HID, NHID, TPC>;
   const long long total = (long long)p.B * p.n_local;
   const unsigned grid = (unsigned)((total + G::THREADS - 1) / G::THREADS);
@@ -497,10 +507,15 @@ static cudaError_t launch_tc(const RolloutParams &p, cudaStream_t st, const floa
     for (int k = 0; k < HID; k++) sum += (double)host_theta_t[G::TH_WL + k * 4 + j];
     ep.b_last[j] = (float)sum;
   }
-  static int smem_bytes = 0;  // decided once per instantiation
+  // decided once per instantiation AND device: cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute
+  // (a second context on another GPU of the same process would otherwise launch without the opt-in)
+  static int smem_bytes_dev[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int &smem_bytes = smem_bytes_dev[dev & 63];
   if (smem_bytes == 0) {
     cudaFuncAttributes fa;
-    cudaError_t e = cudaFuncGetAttributes(&fa, tc::rollout_tc_kernel<HID, NHID, TPC>);
+    cudaError_t e = cudaFuncGetAttributes(&fa, tc::rollout_tc_kernel<HID, NHID, TPC, FUSED>);
     if (e != cudaSuccess) return e;
     int bytes = G::SMEM_BYTES;
     const long long tmem_ctas = 512 / (G::TMEM_COLS * G::TPC);  // CTAs per SM the tensor memory admits
@@ -508,13 +523,18 @@ static cudaError_t launch_tc(const RolloutParams &p, cudaStream_t st, const floa
     const bool smem_admits_more = (long long)(bytes + 2048) * (tmem_ctas + 1) <= 228 * 1024;
     if (regs_admit_more && smem_admits_more) bytes = ((228 / (int)(tmem_ctas + 1)) - 1) * 1024;  // keep TMEM the only limiter
     if (bytes > 48 * 1024) {
-      e = cudaFuncSetAttribute(tc::rollout_tc_kernel<HID, NHID, TPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+      e = cudaFuncSetAttribute(tc::rollout_tc_kernel<HID, NHID, TPC, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
       if (e != cudaSuccess) return e;
     }
     smem_bytes = bytes;
   }
-  tc::rollout_tc_kernel<HID, NHID, TPC><<<grid, G::THREADS, smem_bytes, st>>>(p, ep);
+  tc::rollout_tc_kernel<HID, NHID, TPC, FUSED><<<grid, G::THREADS, smem_bytes, st>>>(p, ep);
   return cudaGetLastError();
+}
+
+template <int HID, int NHID, int TPC>
+static cudaError_t launch_tc(const RolloutParams &p, cudaStream_t st, const float *host_theta_t) {
+  return p.fused_noise ? launch_tc_f<HID, NHID, TPC, true>(p, st, host_theta_t) : launch_tc_f<HID, NHID, TPC, false>(p, st, host_theta_t);
 }
 
 cudaError_t launch_rollout_nn32_tc(const RolloutParams &p, cudaStream_t st, const float *host_theta_t) { return launch_tc<32, 2, 1>(p, st, host_theta_t); }

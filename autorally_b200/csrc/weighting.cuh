@@ -7,38 +7,14 @@
 #pragma once
 #include "device_common.cuh"
 #include "dynamics.cuh"
+#include "philox.cuh"
 #include "warp_mlp.cuh"
 
 namespace mppi {
 
 // ------------------------------------------------------------------------------ sampler ----
-// Philox4x32-10 (Salmon et al., SC'11).  Stream definition: counter = (q, r, call, b)
-// with q the timestep pair (t = 2q, 2q+1), r the GLOBAL rollout index, call the compute-call
-// counter and b the controller; key = seed.  The 4 outputs become eps[r][2q..2q+1][0..1] by
-// Box-Muller, so one thread writes one aligned float4 and a warp writes 512 contiguous bytes.
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
-                                              uint32_t k1, uint32_t (&out)[4]) {
-#pragma unroll
-  for (int r = 0; r < 10; r++) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-    c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
-    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-  }
-  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
-}
-
-__device__ __forceinline__ float2 box_muller(uint32_t xa, uint32_t xb) {
-  // radius = sqrt(-2 ln((xa + .5) 2^-32)); angle = 2 pi (xb + .5) 2^-32 - pi
-  const float ua = fmaf((float)xa, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
-  const float ang = fmaf((float)xb, 1.4629180792671596e-09f, -3.14159265358979f + 7.3145903963357981e-10f);
-  float rad;  // MUFU.SQRT: the IEEE sqrtf sequence (Newton step + slow-path call) was a seventh of the sampler's instructions
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-2.0f * __logf(ua)));
-  float sn, cs;
-  __sincosf(ang, &sn, &cs);
-  return make_float2(rad * cs, rad * sn);
-}
-
+// Philox4x32-10 + Box-Muller live in philox.cuh (shared with the rollout kernels that generate their noise in place).
+// One thread writes one aligned float4 (2 timesteps x 2 controls), a warp writes 512 contiguous bytes.
 // Division of an index below 2^31 by a run-time constant as one multiply-high and a shift (the two divisions by Q and
 // n_local were a quarter of the sampler's instructions): with s = ceil(log2 d), M = ceil(2^(31+s) / d) < 2^32 and
 // n (M d - 2^(31+s)) < 2^(31+s) for every n < 2^31, so (n M) >> (31 + s) is exact.
@@ -63,7 +39,7 @@ struct FastDiv {
 // T = 100) from mapped pinned host memory into the device inbox, which replaces a separate H2D copy node in front of
 // the pipeline; the rollout kernel reads the inbox only after this grid has completed.
 __global__ void __launch_bounds__(256) sample_noise_kernel(float *__restrict__ du, int n_local, int r_begin, int T,
-                                                            int B, uint32_t seed_lo, uint32_t seed_hi,
+                                                            int B, int b_begin, uint32_t seed_lo, uint32_t seed_hi,
                                                             const uint32_t *__restrict__ call_ptr,
                                                             const float4 *__restrict__ inbox_src, float4 *__restrict__ inbox_dst,
                                                             int inbox_float4s, FastDiv divQ, FastDiv divN) {
@@ -80,15 +56,13 @@ __global__ void __launch_bounds__(256) sample_noise_kernel(float *__restrict__ d
     for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < utotal; idx += stride) {
       const unsigned g = divQ.div(idx), q = idx - g * uQ;
       const unsigned b = (B == 1) ? 0u : divN.div(g), lr = g - b * un;
-      uint32_t x[4];
-      philox4x32_10(q, (uint32_t)r_begin + lr, call, b, seed_lo, seed_hi, x);
-      const float2 z0 = box_muller(x[0], x[1]), z1 = box_muller(x[2], x[3]);
+      const float4 z = philox_normal4(q, (uint32_t)r_begin + lr, call, (uint32_t)b_begin + b, seed_lo, seed_hi);
       float *dst = du + ((size_t)g * T + 2 * q) * C_DIM;
       if ((T & 1) == 0) {
-        *reinterpret_cast<float4 *>(dst) = make_float4(z0.x, z0.y, z1.x, z1.y);
+        *reinterpret_cast<float4 *>(dst) = z;
       } else {
-        dst[0] = z0.x; dst[1] = z0.y;
-        if (2 * q + 1 < (unsigned)T) { dst[2] = z1.x; dst[3] = z1.y; }
+        dst[0] = z.x; dst[1] = z.y;
+        if (2 * q + 1 < (unsigned)T) { dst[2] = z.z; dst[3] = z.w; }
       }
     }
     return;
@@ -97,15 +71,13 @@ __global__ void __launch_bounds__(256) sample_noise_kernel(float *__restrict__ d
     const int q = (int)(idx % Q);
     const long long g = idx / Q;
     const int lr = (int)(g % n_local), b = (int)(g / n_local);
-    uint32_t x[4];
-    philox4x32_10((uint32_t)q, (uint32_t)(r_begin + lr), call, (uint32_t)b, seed_lo, seed_hi, x);
-    const float2 z0 = box_muller(x[0], x[1]), z1 = box_muller(x[2], x[3]);
+    const float4 z = philox_normal4((uint32_t)q, (uint32_t)(r_begin + lr), call, (uint32_t)(b_begin + b), seed_lo, seed_hi);
     float *dst = du + ((size_t)g * T + 2 * q) * C_DIM;
     if ((T & 1) == 0) {
-      *reinterpret_cast<float4 *>(dst) = make_float4(z0.x, z0.y, z1.x, z1.y);
+      *reinterpret_cast<float4 *>(dst) = z;
     } else {
-      dst[0] = z0.x; dst[1] = z0.y;
-      if (2 * q + 1 < T) { dst[2] = z1.x; dst[3] = z1.y; }
+      dst[0] = z.x; dst[1] = z.y;
+      if (2 * q + 1 < T) { dst[2] = z.z; dst[3] = z.w; }
     }
   }
 }

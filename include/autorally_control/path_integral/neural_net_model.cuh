@@ -129,7 +129,9 @@ class NeuralNetModel : public Managed {
       for (int j = 0; j < net_structure_[l + 1]; j++) biases_[l](j, 0) = data[off + j];
       off += net_structure_[l + 1];
     }
-    // the reference leaves the upload to the next computeControl's paramsToDevice(); same here
+    // The reference re-uploads on every computeControl (model_->paramsToDevice(), PI/mppi_controller.cu:603-604); here the
+    // controllers upload only when the parameter version changed, so the swap has to repack and bump it now.
+    paramsToDevice();
   }
 
   void printParamVec() {

@@ -43,20 +43,18 @@ enum {
 
 enum { MPPI_DYNAMICS_NN = 0, MPPI_DYNAMICS_BF = 1 };
 
-/* Rollout-kernel variants (mppi_config.rollout_variant).  AUTO picks by problem size: 6-32-32-4 up to 16384 rollouts
- * HALF16, above TENSOR; 6-64-64-64-64-4 always TENSOR; basis functions THREAD1.  A network whose folded biases would
- * leave the FP32 range in the tensor kernel's e^(2b) constants (|b| >= 40) runs on the FP32 kernels instead. */
+/* Rollout-kernel variants (mppi_config.rollout_variant).  AUTO picks by network and problem size: 6-32-32-4 up to 16384
+ * rollouts HALF16, above TENSOR; 6-64-64-64-64-4 always TENSOR; any other layer pack (widths <= 128) GENERIC; basis
+ * functions THREAD1.  A network whose folded biases would leave the FP32 range in the tensor kernel's e^(2b) constants
+ * (|b| >= 40) runs on the FP32 kernels instead.  The numeric values are stable (3-8 were experimental designs of round 1
+ * and are retired). */
 enum {
   MPPI_ROLLOUT_AUTO = 0,
   MPPI_ROLLOUT_THREAD1 = 1, /* one rollout per thread, weights broadcast from shared memory */
-  MPPI_ROLLOUT_THREAD2 = 2, /* two rollouts per thread (register-tiled), weights from shared memory */
-  MPPI_ROLLOUT_SPLIT8 = 3,  /* one rollout across 8 lanes, costs replicated in the lanes */
-  MPPI_ROLLOUT_CONST1 = 4,  /* reserved: weights as constant-bank operands (measured no faster) */
-  MPPI_ROLLOUT_LANES8 = 5,  /* one rollout across 8 / 16 / 32 lanes, cost evaluation deferred and */
-  MPPI_ROLLOUT_LANES16 = 6, /* spread over the lanes: the latency configurations (1920 rollouts -> 32) */
-  MPPI_ROLLOUT_LANES32 = 7,
+  MPPI_ROLLOUT_THREAD2 = 2, /* two rollouts per thread (register-tiled FFMA2), weights from shared memory */
   MPPI_ROLLOUT_HALF16 = 9,  /* one rollout per half-warp, FFMA2 over neuron pairs, deferred running mean: the latency default */
-  MPPI_ROLLOUT_TENSOR = 10  /* one rollout per thread, layer contractions on tcgen05 (FP16 hi/lo split, A in tensor memory) */
+  MPPI_ROLLOUT_TENSOR = 10, /* one rollout per thread, layer contractions on tcgen05 (FP16 hi/lo split, A in tensor memory) */
+  MPPI_ROLLOUT_GENERIC = 11 /* run-time layer pack (NeuralNetModel<7,2,3,6,...,4>, widths <= 128): one rollout per warp, FP32 */
 };
 
 /* Replaces the MPPIController template/ctor arguments (PI/mppi_controller.cuh:52-53,101-102) plus the
@@ -75,6 +73,7 @@ typedef struct mppi_config {
   int bdim_x, bdim_y;   /* reference block shape; informational, kept for API parity */
   int device;           /* CUDA device ordinal, -1 = current device */
   int rollout_variant;  /* MPPI_ROLLOUT_* */
+  int controller_begin; /* batched mode sharded over GPUs: global index of this context's controller 0 (Philox counter) */
   uint64_t seed;        /* Philox key; the reference seeds cuRAND with 1234 (:331) */
 } mppi_config;
 
@@ -131,6 +130,11 @@ int mppi_set_gamma(mppi_ctx *ctx, float gamma);
 int mppi_set_noise(mppi_ctx *ctx, const float *eps, size_t count);
 int mppi_use_sampler(mppi_ctx *ctx);
 int mppi_seed(mppi_ctx *ctx, uint64_t seed, uint32_t call_counter);
+/* Where the sampled noise is produced: 1 = inside the rollout kernel (no separate sampler launch, no noise round trip
+ * through HBM), 0 = by the stand-alone sampler kernel into the [rollouts x T x 2] buffer, -1 = automatic (in place for the
+ * throughput kernels, the sampler kernel for the latency kernels).  Both draw the same Philox stream: results are
+ * bit-identical.  Ignored while injected noise is in use. */
+int mppi_set_fused_noise(mppi_ctx *ctx, int mode);
 /* Runs only the sampler into the noise buffer and copies it out (tests). */
 int mppi_sample_noise(mppi_ctx *ctx, float *eps_out /* [B][rollout_count][T][2] or NULL */);
 

@@ -5,15 +5,17 @@
  * loads or calls this file.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs may use it, and there only as the checker / the CPU baseline.
  *
- * Parity status: PARTIALLY PINNED.  The reference (rdesc/autorally) ships no tests, golden vectors
- * or known-answer fixtures for this path, and its C++/CUDA sources cannot be
- * built here without ROS/Eigen/cnpy/OpenCV.  What *is* pinned:
- *   - the dynamics (R7/R9: MLP forward + kinematics + Euler step) against the reference's own
- *     Python model (ml_pipeline/utils.py setup_model + npz_to_torch_model + compute_state_ders),
- *     imported unmodified by tests/golden/make_golden.py; vectors in tests/golden/.
- *   - the Philox4x32-10 core against the published Random123 known-answer vectors.
- * Everything else (costs, bookkeeping, weighting, smoothing) is restated from reading the reference
- * and is "parity unpinned" in the sense of the task statement.
+ * Parity status: PINNED.  The reference (rdesc/autorally) ships no tests, golden vectors or known-answer
+ * fixtures for this path, so its own compiled code is the authority:
+ *   - oracle/refbuild.py compiles the reference's MPPI sources from /root/reference for sm_100a
+ *     (oracle/_ref/libautorally_ref.so); tests/golden/ref_gpu_golden.npz holds inputs + outputs of that
+ *     library (made on a B200 by tests/golden/make_ref_gpu_golden.py) and pins costs, bookkeeping,
+ *     weighting, smoothing and the nominal trajectory of this file in the CPU suite
+ *     (tests/test_oracle_golden.py); tests/test_reference_gpu.py repeats the comparison live on the GPU box;
+ *   - the dynamics (R7/R9: MLP forward + kinematics + Euler step) are also pinned against the reference's
+ *     Python model (ml_pipeline/utils.py, imported unmodified by tests/golden/make_golden.py);
+ *   - the Philox4x32-10 core against the published Random123 known-answer vectors (R1 is defined on
+ *     injected identical noise: the generator changes from cuRAND XORWOW to Philox by specification).
  *
  * All citations are relative to /root/reference/autorally_control/include/autorally_control/
  * path_integral/ ("PI/").  Arithmetic is float32 with the reference's double-precision spots kept.

@@ -219,3 +219,16 @@ def sample_noise(seed, call, r_begin, r_count, T, controller=0):
     eps = np.zeros((r_count, T, 2), np.float32)
     lib().oracle_sample_noise(ctypes.c_uint64(seed), ctypes.c_uint32(call), ctypes.c_uint32(controller), int(r_begin), int(r_count), int(T), _fp(eps))
     return eps
+
+
+def make_oracle(kind, models, costmap, cp, tag="autorally_nnet", negate_yaw_der=True, bdim_y=None, theta=None, structure=None):
+    """The oracle configured like the reference's main() configures its controller (launch-file defaults)."""
+    from autorally_b200.params import BF_DEFAULTS, NN_DEFAULTS
+    d = NN_DEFAULTS if kind == "nn" else BF_DEFAULTS
+    if kind == "nn":
+        if theta is None:
+            theta, structure = models[tag + "_theta"], models[tag + "_structure"]
+        return Oracle("nn", theta, structure, dt=1.0 / d["hz"], negate_yaw_der=negate_yaw_der,
+                      control_ranges=d["control_ranges"], cost_params=cp, costmap=costmap)
+    return Oracle("bf", models["basis_function_W"], None, dt=1.0 / d["hz"], control_ranges=d["control_ranges"],
+                  bdim_y=bdim_y if bdim_y is not None else d["bdim"][1], cost_params=cp, costmap=costmap)

@@ -71,10 +71,13 @@ struct RefBase {
   virtual int compute(const float *state, float *eps_out, float *U_out, float *ss, float *cs, float *scalars, float *weights) = 0;
   virtual int rollout_costs(const float *state, const float *U, const float *eps, float *costs, float *V) = 0;
   virtual int time_compute(const float *state, int reps, float *ms_per_call) = 0;
+  virtual int time_kernels(const float *state, int reps, float *ms4) = 0;
 };
 
 typedef NeuralNetModel<7, 2, 3, 6, 32, 32, 4> RefNN;
 typedef NeuralNetModel<7, 2, 3, 6, 64, 64, 64, 64, 4> RefNN64;  // SRC/params/models/wider_deeper_network_08_20_2020.npz
+typedef NeuralNetModel<7, 2, 3, 6, 16, 16, 4> RefNN16;  // layer packs without a dedicated kernel in the product: the
+typedef NeuralNetModel<7, 2, 3, 6, 48, 4> RefNN48;      // reference's variadic template takes any (PI/neural_net_model.cuh:48-52)
 typedef GeneralizedLinear<CarBasisFuncs, 7, 2, 25, CarKinematics, 3> RefBF;
 
 template <class MODEL, int ROLLOUTS, int BX, int BY>
@@ -182,6 +185,8 @@ struct RefImpl : RefBase {
   }
 
   // Wall-clock of the reference's computeControl on this GPU (its own host syncs and memcpys included).
+  int time_kernels(const float *state, int reps, float *ms4) override;
+
   int time_compute(const float *state, int reps, float *ms_per_call) override {
     Eigen::Matrix<float, 7, 1> s;
     for (int i = 0; i < 7; i++) s(i) = state[i];
@@ -206,6 +211,61 @@ struct RefImpl : RefBase {
     return 0;
   }
 };
+
+template <class MODEL, int ROLLOUTS, int BX, int BY>
+int RefImpl<MODEL, ROLLOUTS, BX, BY>::time_kernels(const float *state, int reps, float *ms4) {
+  // Device time of the reference's four GPU stages, each launched exactly as computeControl launches it
+  // (PI/mppi_controller.cu:612-660) but through cudaLaunchKernel with pointers to the live model / cost objects, so that
+  // the by-value kernel arguments are byte copies instead of C++ copies (launchRolloutKernel's `*mppi_costs` argument
+  // deep-copies the std::vector<float4> costmap on the host at every launch, PI/mppi_controller.cu:285-286): what is
+  // timed here is the kernels alone.  ms4 = {curandGenerateNormal, rolloutKernel, normExpKernel, weightedReductionKernel}.
+  const size_t count = (size_t)N * T * 2;
+  costs->paramsToDevice();
+  model->paramsToDevice();
+  cudaMemcpy(ctrl->state_d_, state, 7 * sizeof(float), cudaMemcpyHostToDevice);
+  cudaMemcpy(ctrl->U_d_, ctrl->U_.data(), 2 * T * sizeof(float), cudaMemcpyHostToDevice);
+  std::vector<cudaEvent_t> ev(8 * (size_t)reps);
+  for (auto &e : ev) cudaEventCreate(&e);
+  int num_timesteps = T, opt_delay = opt_stride;
+  float gamma = ctrl->gamma_, baseline = 0.0f, normalizer = 1.0f;
+  void *roll_args[] = {&num_timesteps, &ctrl->state_d_, &ctrl->U_d_, &ctrl->du_d_, &ctrl->nu_d_, &ctrl->traj_costs_d_, model, costs, &opt_delay};
+  void *norm_args[] = {&ctrl->traj_costs_d_, &gamma, &baseline};
+  void *wred_args[] = {&ctrl->traj_costs_d_, &ctrl->du_d_, &ctrl->nu_d_, &normalizer, &num_timesteps};
+  const dim3 rb(BX, BY, 1), rg((N - 1) / BX + 1, 1, 1), nb(BX, 1, 1), ng((N - 1) / BX + 1, 1, 1), wb((N - 1) / 64 + 1, 1, 1), wg(T, 1, 1);
+  std::vector<float> host_costs(N);
+  for (int r = -1; r < reps; r++) {  // r = -1: warm-up, and the baseline / normaliser of a real call
+    cudaEvent_t *e = r < 0 ? nullptr : &ev[8 * (size_t)r];
+    if (e) cudaEventRecord(e[0], 0);
+    curandGenerateNormal(ctrl->gen_, ctrl->du_d_, count, 0.0f, 1.0f);  // the controller's own generator (PI/mppi_controller.cu:612)
+    if (e) { cudaEventRecord(e[1], 0); cudaEventRecord(e[2], 0); }
+    cudaLaunchKernel((const void *)rolloutKernel<MODEL, MPPICosts, ROLLOUTS, BX, BY>, rg, rb, roll_args, 0, 0);
+    if (e) cudaEventRecord(e[3], 0);
+    if (r < 0) {
+      cudaMemcpy(host_costs.data(), ctrl->traj_costs_d_, N * sizeof(float), cudaMemcpyDeviceToHost);
+      baseline = host_costs[0];
+      for (int i = 0; i < N; i++) baseline = host_costs[i] < baseline ? host_costs[i] : baseline;
+      normalizer = 0.0f;
+      for (int i = 0; i < N; i++) normalizer += expf(-gamma * (host_costs[i] - baseline));
+    }
+    if (e) cudaEventRecord(e[4], 0);
+    cudaLaunchKernel((const void *)normExpKernel<MODEL, MPPICosts, ROLLOUTS, BX, BY>, ng, nb, norm_args, 0, 0);
+    if (e) { cudaEventRecord(e[5], 0); cudaEventRecord(e[6], 0); }
+    cudaLaunchKernel((const void *)weightedReductionKernel<MODEL, MPPICosts, ROLLOUTS, BX, BY>, wg, wb, wred_args, 0, 0);
+    if (e) cudaEventRecord(e[7], 0);
+  }
+  for (int r = -1; r < reps; r++) curandGenerateNormal(twin, eps_d, count, 0.0f, 1.0f);  // keep the twin generator in step
+  cudaError_t err = cudaDeviceSynchronize();
+  if (err != cudaSuccess) return (int)err;
+  for (int k = 0; k < 4; k++) ms4[k] = 0.0f;
+  for (int r = 0; r < reps; r++)
+    for (int k = 0; k < 4; k++) {
+      float ms = 0.0f;
+      cudaEventElapsedTime(&ms, ev[8 * (size_t)r + 2 * k], ev[8 * (size_t)r + 2 * k + 1]);
+      ms4[k] += ms / reps;
+    }
+  for (auto &e : ev) cudaEventDestroy(e);
+  return 0;
+}
 
 template <class NN, int NLAYERS, int ROLLOUTS, int BX, int BY>
 RefBase *make_nn_t(const int *widths, const float *theta, int negate_yaw, const float *lo_hi, const float *costmap, int w, int h,
@@ -250,6 +310,14 @@ RefBase *make_nn64(const float *theta, int negate_yaw, const float *lo_hi, const
   return make_nn_t<RefNN64, 6, ROLLOUTS, BX, BY>(widths, theta, negate_yaw, lo_hi, costmap, w, h, cp, nu, init_u, hz, T, opt_stride, gamma, num_iters, rc);
 }
 
+template <class NN, int ROLLOUTS, int BX, int BY, int... WIDTHS>
+RefBase *make_nn_pack(const float *theta, int negate_yaw, const float *lo_hi, const float *costmap, int w, int h,
+                      const ref_cost_params *cp, const float *nu, const float *init_u, int hz, int T, int opt_stride, float gamma,
+                      int num_iters, int *rc) {
+  static const int widths[sizeof...(WIDTHS)] = {WIDTHS...};
+  return make_nn_t<NN, (int)sizeof...(WIDTHS), ROLLOUTS, BX, BY>(widths, theta, negate_yaw, lo_hi, costmap, w, h, cp, nu, init_u, hz, T, opt_stride, gamma, num_iters, rc);
+}
+
 template <int ROLLOUTS, int BX, int BY>
 RefBase *make_bf(const float *theta, const float *lo_hi, const float *costmap, int w, int h, const ref_cost_params *cp,
                  const float *nu, const float *init_u, int hz, int T, int opt_stride, float gamma, int num_iters, int *rc) {
@@ -268,7 +336,7 @@ RefBase *make_bf(const float *theta, const float *lo_hi, const float *costmap, i
 
 extern "C" {
 
-enum { REF_NN_1920 = 0, REF_BF_2560 = 1, REF_NN_256 = 2, REF_NN_4096 = 3, REF_BF_256 = 4, REF_NN64_1920 = 5 };
+enum { REF_NN_1920 = 0, REF_BF_2560 = 1, REF_NN_256 = 2, REF_NN_4096 = 3, REF_BF_256 = 4, REF_NN64_1920 = 5, REF_NN16_1920 = 6, REF_NN48_1920 = 7 };
 
 const char *ref_version(void) { return "rdesc/autorally MPPIController (reference sources, sm_100a build, shimmed host libraries)"; }
 
@@ -291,6 +359,9 @@ int ref_create(int kind, const float *theta, int negate_yaw, const float *lo_hi,
     case REF_NN_4096: r = make_nn<4096, 8, 16>(theta, negate_yaw, lo_hi, costmap, w, h, cp, nu, init_u, hz, T, opt_stride, gamma, num_iters, &rc); break;
     case REF_BF_256: r = make_bf<256, 16, 4>(theta, lo_hi, costmap, w, h, cp, nu, init_u, hz, T, opt_stride, gamma, num_iters, &rc); break;
     case REF_NN64_1920: r = make_nn64<1920, 8, 16>(theta, negate_yaw, lo_hi, costmap, w, h, cp, nu, init_u, hz, T, opt_stride, gamma, num_iters, &rc); break;
+    // NeuralNetModel<7,2,3,6,16,16,4> and <7,2,3,6,48,4>: arbitrary layer packs (weights supplied by the caller)
+    case REF_NN16_1920: r = make_nn_pack<RefNN16, 1920, 8, 16, 6, 16, 16, 4>(theta, negate_yaw, lo_hi, costmap, w, h, cp, nu, init_u, hz, T, opt_stride, gamma, num_iters, &rc); break;
+    case REF_NN48_1920: r = make_nn_pack<RefNN48, 1920, 8, 16, 6, 48, 4>(theta, negate_yaw, lo_hi, costmap, w, h, cp, nu, init_u, hz, T, opt_stride, gamma, num_iters, &rc); break;
     default: return -1;
   }
   if (rc) { delete r; return rc; }
@@ -314,5 +385,7 @@ int ref_rollout_costs(void *h, const float *state, const float *U, const float *
 int ref_time_compute_control(void *h, const float *state, int reps, float *ms_per_call) {
   return static_cast<RefBase *>(h)->time_compute(state, reps, ms_per_call);
 }
+// ms4 = device time of {curandGenerateNormal, rolloutKernel, normExpKernel, weightedReductionKernel} per computeControl iteration
+int ref_time_kernels(void *h, const float *state, int reps, float *ms4) { return static_cast<RefBase *>(h)->time_kernels(state, reps, ms4); }
 
 }  // extern "C"

@@ -14,8 +14,9 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_ref", "libautorally_ref.so")
 
-REF_NN_1920, REF_BF_2560, REF_NN_256, REF_NN_4096, REF_BF_256, REF_NN64_1920 = 0, 1, 2, 3, 4, 5
-KIND_ROLLOUTS = {REF_NN_1920: 1920, REF_BF_2560: 2560, REF_NN_256: 256, REF_NN_4096: 4096, REF_BF_256: 256, REF_NN64_1920: 1920}
+REF_NN_1920, REF_BF_2560, REF_NN_256, REF_NN_4096, REF_BF_256, REF_NN64_1920, REF_NN16_1920, REF_NN48_1920 = 0, 1, 2, 3, 4, 5, 6, 7
+KIND_ROLLOUTS = {REF_NN_1920: 1920, REF_BF_2560: 2560, REF_NN_256: 256, REF_NN_4096: 4096, REF_BF_256: 256, REF_NN64_1920: 1920,
+                 REF_NN16_1920: 1920, REF_NN48_1920: 1920}
 
 c_float_p = ctypes.POINTER(ctypes.c_float)
 _lib = None
@@ -114,6 +115,15 @@ class ReferenceController:
         if rc != 0:
             raise RuntimeError("ref_rollout_costs failed: %d" % rc)
         return costs, V
+
+    def time_kernels(self, state, reps=20):
+        """Device time (ms) of the reference's four GPU stages per computeControl iteration, kernels alone:
+        {curand, rollout, normexp, weighted_reduction} (oracle/ref_harness.cu::time_kernels)."""
+        ms = np.zeros(4, np.float32)
+        rc = lib().ref_time_kernels(self._h, _fp(_f32(state, 7)), int(reps), _fp(ms))
+        if rc != 0:
+            raise RuntimeError("ref_time_kernels failed: %d" % rc)
+        return dict(curand=float(ms[0]), rollout=float(ms[1]), normexp=float(ms[2]), weighted_reduction=float(ms[3]))
 
     def time_compute_control(self, state, reps=20):
         ms = ctypes.c_float(0)

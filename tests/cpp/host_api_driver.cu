@@ -4,7 +4,7 @@
 // runControlLoop (PI/run_control_loop.cuh:208-225).  Results go to an .npz the pytest side compares
 // with the CPU oracle.
 //
-// usage: host_api_driver <nn|bf> <launch_file> <noise.bin> <out.npz> x y yaw roll ux uy yawrate
+// usage: host_api_driver <nn|bf> <launch_file> <noise.bin> <out.npz> x y yaw roll ux uy yawrate [swap.npz]
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -23,8 +23,21 @@
 
 using namespace autorally_control;
 
+template <class M>
+void swap_model(M *model, const std::string &path) {
+  npz::Archive a = npz::load(path);
+  const npz::Array &d = a.at("description"), &v = a.at("data");
+  std::vector<int> description(d.num_vals());
+  std::vector<float> data(v.num_vals());
+  for (size_t i = 0; i < description.size(); i++) description[i] = (int)d.at(i);
+  for (size_t i = 0; i < data.size(); i++) data[i] = (float)v.at(i);
+  model->updateModel(description, data);
+}
+template <>
+void swap_model(GeneralizedLinear<CarBasisFuncs, 7, 2, 25, CarKinematics, 3> *, const std::string &) {}
+
 template <class Controller, class DynamicsModel>
-int run(const std::string &launch, const std::string &noise_path, const std::string &out_path, const float *st) {
+int run(const std::string &launch, const std::string &noise_path, const std::string &out_path, const float *st, const std::string &swap_path) {
   std::map<std::string, XmlRpc::XmlRpcValue> params;
   loadParams(&params, launch);
   MPPICosts *costs = new MPPICosts(&params);
@@ -77,6 +90,18 @@ int run(const std::string &launch, const std::string &noise_path, const std::str
   w.add("U2", U2.data(), {(size_t)T, 2}); w.add("state_solution2", ss2.data(), {(size_t)T, 7});
   const float tc2 = ctl->getComputedTrajectoryCost();
   w.add("trajectory_cost2", &tc2, {1});
+  // ---- model hot swap (updateModel: the flattened /model_updater/model message) must reach the DEVICE: the rollouts and the
+  //      nominal trajectory of the next computeControl run on the new weights ----
+  if (!swap_path.empty()) {
+    swap_model(model, swap_path);
+    std::vector<float> Uin = ctl->getControlSequenceU();
+    w.add("U_in_swap", Uin.data(), {(size_t)T, 2});
+    ctl->setNoise(eps.data(), per_call);
+    ctl->computeControl(state);
+    std::vector<float> Us = ctl->getControlSequenceU(), sss = ctl->getStateSeq(), rcs = ctl->getRolloutCosts();
+    w.add("U_swap", Us.data(), {(size_t)T, 2}); w.add("state_solution_swap", sss.data(), {(size_t)T, 7});
+    w.add("rollout_costs_swap", rcs.data(), {rcs.size()});
+  }
   // ---- updateControlNoise + cutThrottle + the Philox sampler path ----
   const float wide[2] = {0.4f, 0.5f};
   ctl->updateControlNoise(wide);
@@ -102,9 +127,9 @@ int main(int argc, char **argv) {
   if (kind == "nn") {
     typedef NeuralNetModel<7, 2, 3, 6, 32, 32, 4> DynamicsModel;                      // SRC/path_integral_main.cu:66-69
     typedef MPPIController<DynamicsModel, MPPICosts, 1920, 8, 16> Controller;
-    return run<Controller, DynamicsModel>(argv[2], argv[3], argv[4], st);
+    return run<Controller, DynamicsModel>(argv[2], argv[3], argv[4], st, argc > 12 ? argv[12] : "");
   }
   typedef GeneralizedLinear<CarBasisFuncs, 7, 2, 25, CarKinematics, 3> DynamicsModel;  // :71-74
   typedef MPPIController<DynamicsModel, MPPICosts, 2560, 16, 4> Controller;
-  return run<Controller, DynamicsModel>(argv[2], argv[3], argv[4], st);
+  return run<Controller, DynamicsModel>(argv[2], argv[3], argv[4], st, argc > 12 ? argv[12] : "");
 }

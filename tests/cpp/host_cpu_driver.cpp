@@ -15,6 +15,9 @@
 #include <autorally_control/path_integral/car_kinematics.cuh>
 #include <autorally_control/path_integral/generalized_linear.cuh>
 #include <autorally_control/ddp/ddp_feedback.h>
+#define private public  // the reference's own test idiom (autorally_core/test/serialSensorInterfaceTest.cpp:43-61): U_, control_hist_
+#include <autorally_control/path_integral/mppi_controller.cuh>
+#undef private
 
 using namespace autorally_control;
 
@@ -80,6 +83,24 @@ int main(int argc, char **argv) {
     MPPICosts c(&p);
     printf("%d %d %.9g %.9g %.9g %.9g %.9g %.9g %lu %lu\n", c.width(), c.height(), c.params_.r_c1.x, c.params_.r_c2.y, c.params_.trs.x,
            c.params_.trs.y, c.params_.desired_speed, c.params_.boundary_threshold, c.paramsVersion(), c.mapVersion());
+    return 0;
+  }
+  if (cmd == "slide") {
+    // slideControlAndStateSeq(stride) of the drop-in MPPIController template (host logic only; without a GPU the context
+    // creation fails, which the class reports and survives): slide stride init_u0 init_u1 hist[4] U[2T] -> hist[4] U[2T]
+    const int stride = atoi(argv[2]), T = (argc - 9) / 2;
+    float init_u[2] = {(float)atof(argv[3]), (float)atof(argv[4])}, nu[2] = {0.275f, 0.3f};
+    float2 rng[2] = {make_float2(-.99, .99), make_float2(-.99, .65)};
+    typedef NeuralNetModel<7, 2, 3, 6, 32, 32, 4> Model;
+    Model model(0.02f, rng);
+    MPPICosts costs(4, 4);
+    MPPIController<Model, MPPICosts, 1920, 8, 16> ctl(&model, &costs, nu, init_u, 50, T, stride, 0.15f, 1);
+    for (int i = 0; i < 4; i++) ctl.control_hist_[i] = (float)atof(argv[5 + i]);
+    for (int i = 0; i < 2 * T; i++) ctl.U_[i] = (float)atof(argv[9 + i]);
+    ctl.slideControlAndStateSeq(stride);
+    for (int i = 0; i < 4; i++) printf("%.9g ", ctl.control_hist_[i]);
+    for (int i = 0; i < 2 * T; i++) printf("%.9g ", ctl.U_[i]);
+    printf("\n");
     return 0;
   }
   if (cmd == "ddp_toy") {

@@ -81,5 +81,9 @@ def test_model_hot_swap_through_the_update_model_message(tmp_path, models, costm
     same = run_loop(tmp_path, models, costmap, "nn", n, pose, swap=(models["autorally_nnet_theta"], models["autorally_nnet_structure"], k))["states"]
     np.testing.assert_array_equal(same, base)
     other = run_loop(tmp_path, models, costmap, "nn", n, pose, swap=(models["gazebo_nnet_theta"], models["gazebo_nnet_structure"], k))["states"]
-    np.testing.assert_array_equal(other[:k + 1], base[:k + 1])
+    # the swap is applied before computeControl of iteration k: rows < k are untouched; row k is still the pre-swap state, but
+    # the arbitration of iteration k (run on the NEW model, on the device) may hand over the other controller's copy of it
+    # (measured state vs predicted state: equal to float rounding)
+    np.testing.assert_array_equal(other[:k], base[:k])
+    np.testing.assert_allclose(other[k], base[k], rtol=1e-5, atol=1e-6)
     assert np.abs(other[k + 5:] - base[k + 5:]).max() > 1e-3

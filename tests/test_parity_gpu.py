@@ -9,10 +9,13 @@ Such rollouts sit ~10^2..10^4 above the baseline and carry zero weight.  The tes
 >= 99% of the rollouts to agree within 1e-4 (typically > 99.9%), require every outlier to be explained by
 whole discrete quanta, and hold the baseline and the weighted controls to the full tolerance.
 """
+import os
+
 import numpy as np
 import pytest
 
-from tests.common import cost_params_for, default_state, make_context, make_oracle, straight_controls, top_state, warm_controls
+from tests.common import (cost_params_for, default_state, make_context, make_oracle, random_network, straight_controls, top_state,
+                          warm_controls)
 
 pytestmark = pytest.mark.gpu
 
@@ -21,6 +24,28 @@ NU = np.array([0.275, 0.3], np.float32)
 
 def rel_err(a, b, floor=1.0):
     return np.abs(a - b) / (floor + np.abs(b))
+
+
+# Truly relative control errors are REPORTED and loosely bounded, not held to 1e-4: U = sum_r w_r V_r / Z with
+# w_r = exp(-gamma (c_r - b)) is a softmax over float32 costs.  One ulp of a crashed rollout's cost (c ~ 9000: 1e-3
+# absolute) moves its weight by gamma * 1e-3 = 1.5e-4 relative and U by up to 1.5e-4 * |V_r - U| ~ 4e-5 absolute, so two
+# correct float32 implementations (the reference and the oracle included) differ by more than 1e-4 of a control of
+# magnitude 0.01..0.1.  The 1e-4 bar is held on |a - b| / (1 + |b|) everywhere.
+TRUE_REL_BOUND = 3e-3
+
+
+def true_rel_err(a, b, min_abs=1e-2):
+    """max |a - b| / |b| over the elements with |b| > min_abs."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    m = np.abs(b) > min_abs
+    return float(np.max(np.abs(a[m] - b[m]) / np.abs(b[m]))) if m.any() else 0.0
+
+
+def check_scalars(got, want, tol=1e-4):
+    """baseline, normalizer_ and trajectory_cost_ (PI/mppi_controller.cu:627-652) to the full tolerance, truly relative."""
+    for k in [k for k in ("baseline", "normalizer", "trajectory_cost") if k in got]:
+        g, w = float(np.asarray(got[k]).reshape(-1)[0]), float(np.asarray(want[k]).reshape(-1)[0])
+        assert abs(g - w) <= tol * max(abs(w), 1e-30), "%s: got %.9g want %.9g (rel %.3g)" % (k, g, w, abs(g - w) / max(abs(w), 1e-30))
 
 
 def run_pair(kind, models, costmap, N, T=100, speed=5.0, seed=11, variant=0, cp_over=None, tag="autorally_nnet",
@@ -67,16 +92,17 @@ def check_pair(want, got, cost_tol=1e-4, u_tol=1e-4):
     assert agree.mean() >= 0.995, "crash flags disagree on %.2f%% of rollouts" % (100 * (1 - agree.mean()))
     T = want["V"].shape[1]
     check_costs(got["costs"], want["costs"], T, cost_tol)
-    assert abs(got["baseline"] - want["baseline"]) <= cost_tol * (1 + abs(want["baseline"]))
-    assert rel_err(got["normalizer"], want["normalizer"]).max() < 1e-3
-    assert rel_err(got["trajectory_cost"], want["trajectory_cost"]).max() < 1e-3
+    check_scalars(got, want, cost_tol)
     assert rel_err(got["U"], want["U"]).max() < u_tol, "max control rel err %.3g" % rel_err(got["U"], want["U"]).max()
+    tr = true_rel_err(got["U"], want["U"])
+    print("control error: max |dU| / (1 + |U|) = %.3g, true relative over |u| > 1e-2 = %.3g" % (rel_err(got["U"], want["U"]).max(), tr))
+    assert tr < TRUE_REL_BOUND, "true relative control error %.3g over |u| > 1e-2" % tr
     assert rel_err(got["state_solution"], want["state_solution"]).max() < 1e-4
     assert rel_err(got["control_solution"], want["control_solution"]).max() < u_tol
     assert got["launches"] >= 3
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 5, 6, 7, 9, 10])
+@pytest.mark.parametrize("variant", [1, 2, 9, 10])
 @pytest.mark.parametrize("speed", [0.0, 4.0, 8.0])
 def test_nn_1920x100_matches_oracle(models, costmap, variant, speed):
     """BASELINE config 2: path_integral_nn, 1920 rollouts x 100 steps, synthetic ellipse costmap."""
@@ -84,7 +110,7 @@ def test_nn_1920x100_matches_oracle(models, costmap, variant, speed):
     check_pair(want, got)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 5, 7, 9, 10])
+@pytest.mark.parametrize("variant", [1, 2, 9, 10])
 @pytest.mark.parametrize("gamma", [0.15, 0.01])
 def test_nn_spread_weights_match_oracle(models, costmap, variant, gamma):
     """Flat top of the ellipse at 4 m/s: ~30% of the rollouts survive and the weights are spread over many
@@ -380,3 +406,264 @@ def test_wider_deeper_65536_two_tile_ctas_agree_with_fp32_kernel(models, costmap
     assert abs(a["baseline"] - b["baseline"]) <= 3e-4 * (1 + abs(b["baseline"]))
     assert rel_err(a["U"], b["U"]).max() < 3e-4
     assert rel_err(a["state_solution"], b["state_solution"]).max() < 1e-4
+
+
+# ---- round 2: the parity holes of VERDICT r1 ----
+
+def _philox_noise_then_rewind(ctx, seed=1234, call=0):
+    """The N(0,1) draws compute call `call` will consume: run the stand-alone sampler at that counter, then rewind."""
+    ctx.use_sampler()
+    ctx.seed(seed, call)
+    eps = ctx.sample_noise()
+    ctx.seed(seed, call)
+    return eps
+
+
+def test_1m_rollouts_match_the_cpu_oracle(models, costmap):
+    """BASELINE config 4 at FULL size against the CPU oracle (1 048 576 rollouts x 100 steps, ~20 s of oracle time on the
+    host cores): costs, crash flags, the bit-exact bookkeeping of the sampled controls (global noise-free rollout 0,
+    pure-noise tail r >= 0.99 N), baseline, normaliser, trajectory cost, controls, nominal trajectory.  Two CUDA runs
+    against the same oracle answer: AUTO (tensor-core kernel drawing its Philox noise in place) and variant 10 on the
+    same draws injected through mppi_set_noise (noise read from the buffer)."""
+    cp = cost_params_for(costmap)
+    N, T = 1048576, 100
+    state, U = top_state(4.0), straight_controls(T)
+    hist = np.array([0.05, 0.3, 0.02, 0.3], np.float32)
+    with make_context("nn", models, costmap, cp, N) as ctx:
+        eps = _philox_noise_then_rewind(ctx)          # [1, N, T, 2] from sample_noise_kernel
+        assert ctx.resolved_variant() == 10
+        got = ctx.compute_control(state, U, hist)     # the same draws, made inside rollout_tc_kernel
+        got["costs"], got["crash"], got["V"] = ctx.rollout_costs(), ctx.rollout_crash(), ctx.sampled_controls()
+        got["launches"] = ctx.last_launch_count()
+    assert got["launches"] == 3                       # rollouts, weighting, finalize: no sampler launch
+    want = make_oracle("nn", models, costmap, cp).compute_control(state, U, hist, NU, eps.reshape(1, N, T, 2), threads=os.cpu_count() or 8)
+    np.testing.assert_array_equal(got["V"], want["V"])
+    assert want["V"][0, 5, 0] == U[5, 0] and np.array_equal(want["V"][-1, 1:], (eps.reshape(N, T, 2)[-1, 1:] * NU))  # r = 0 and the tail
+    del got["V"]
+    assert (got["crash"] == want["crash"]).mean() >= 0.995
+    check_costs(got["costs"], want["costs"], T, min_ok=0.995)
+    check_scalars({k: got[k] for k in ("baseline", "normalizer")}, {k: want[k] for k in ("baseline", "normalizer")})
+    # sum w^2 / Z is carried by the few best of a million rollouts and squares their weights: 4e-4 measured (tensor-core numerics)
+    assert abs(got["trajectory_cost"] - want["trajectory_cost"]) <= 1e-3 * want["trajectory_cost"]
+    print("1M rollouts: normalizer %.6g (oracle %.6g), trajectory_cost %.6g (oracle %.6g), max |dU|/(1+|U|) %.3g, true rel %.3g" % (
+        got["normalizer"], want["normalizer"], got["trajectory_cost"], want["trajectory_cost"], rel_err(got["U"], want["U"]).max(),
+        true_rel_err(got["U"], want["U"])))
+    assert rel_err(got["U"], want["U"]).max() < 1e-4 and true_rel_err(got["U"], want["U"]) < TRUE_REL_BOUND
+    assert rel_err(got["state_solution"], want["state_solution"]).max() < 1e-4
+    with make_context("nn", models, costmap, cp, N, variant=10) as ctx:
+        ctx.set_noise(eps)
+        inj = ctx.compute_control(state, U, hist)
+        inj_costs = ctx.rollout_costs()
+        assert ctx.last_launch_count() == 3
+    # identical noise, identical kernel arithmetic: drawing in place or reading the buffer must not change a bit
+    np.testing.assert_array_equal(inj_costs, got["costs"])
+    np.testing.assert_array_equal(inj["U"], got["U"])
+
+
+@pytest.mark.parametrize("kind,N,variant", [("nn", 65536, 0), ("nn", 4096, 1), ("nn", 1920, 11), ("bf", 32768, 0)])
+def test_fused_noise_is_bitwise_the_sampler_kernel(models, costmap, kind, N, variant):
+    """Rollout kernels that draw their Philox noise in place use the counters of sample_noise_kernel: every output is
+    bit-identical to the run that reads the sampler kernel's buffer (tensor-core, one-rollout-per-thread, run-time layer
+    and basis-function kernels)."""
+    cp = cost_params_for(costmap, desired_speed=6.0 if kind == "bf" else 8.0)
+    state, U = top_state(4.0), straight_controls(100)
+    res = []
+    for fused in (1, 0):
+        with make_context(kind, models, costmap, cp, N, variant=variant, seed=77) as ctx:
+            ctx.set_fused_noise(fused)
+            ctx.seed(77, 3)
+            a = ctx.compute_control(state, U)
+            b = ctx.compute_control(state, a["U"])  # call counter 4
+            res.append((a, b, ctx.rollout_costs(), ctx.sampled_controls(), ctx.last_launch_count()))
+    assert res[0][4] == 3 and res[1][4] == 4
+    for k in ("U", "state_solution", "baseline", "normalizer", "trajectory_cost"):
+        np.testing.assert_array_equal(res[0][0][k], res[1][0][k])
+        np.testing.assert_array_equal(res[0][1][k], res[1][1][k])
+    np.testing.assert_array_equal(res[0][2], res[1][2])
+    np.testing.assert_array_equal(res[0][3], res[1][3])
+
+
+def test_batched_mpc_4096x256_matches_oracle_on_sampled_controllers(models, costmap):
+    """BASELINE config 5 at FULL size: 4096 independent controllers x 256 rollouts x 100 steps in one context (Philox noise
+    drawn in the kernel, counter = global controller index); 64 controllers spread over the batch are re-run on the CPU oracle
+    with the very draws they consumed."""
+    from autorally_b200.params import ellipse_states
+    cp = cost_params_for(costmap)
+    B, N, T = 4096, 256, 100
+    states = ellipse_states(B)
+    U = np.broadcast_to(warm_controls(T), (B, T, 2)).copy()
+    hist = np.tile(np.array([0.1, 0.3, 0.11, 0.32], np.float32), (B, 1))
+    with make_context("nn", models, costmap, cp, N, num_controllers=B) as ctx:
+        eps = _philox_noise_then_rewind(ctx)   # [B, N, T, 2]
+        got = ctx.compute_control(states, U, hist)
+        costs, V = ctx.rollout_costs(), ctx.sampled_controls()
+        assert ctx.resolved_variant() == 10 and ctx.last_launch_count() == 3
+    o = make_oracle("nn", models, costmap, cp)
+    picks = np.unique(np.concatenate([[0, 1, B - 1], np.random.default_rng(5).choice(B, 61, replace=False)]))
+    worst_u = 0.0
+    for b in picks:
+        want = o.compute_control(states[b], U[b], hist[b], NU, eps[b][None], threads=8)
+        np.testing.assert_array_equal(V[b], want["V"])
+        check_costs(costs[b], want["costs"], T, min_ok=0.98)   # 256 rollouts: 1% is 2.5 rollouts
+        check_scalars({k: got[k][b] for k in ("baseline", "normalizer", "trajectory_cost")}, want)
+        worst_u = max(worst_u, rel_err(got["U"][b], want["U"]).max())
+        assert rel_err(got["state_solution"][b], want["state_solution"]).max() < 1e-4
+    assert worst_u < 1e-4, worst_u
+    assert len(picks) >= 60
+
+
+def test_controller_sharding_is_independent_of_the_split(models, costmap):
+    """Batched-MPC mode sharded over GPUs: controller k draws the noise of GLOBAL controller k whichever context holds it
+    (mppi_config.controller_begin), so two half-batches reproduce the full batch bit for bit."""
+    from autorally_b200.params import ellipse_states
+    cp = cost_params_for(costmap)
+    B, N, T = 128, 256, 100
+    states = ellipse_states(B)
+    U = np.broadcast_to(straight_controls(T), (B, T, 2)).copy()
+    with make_context("nn", models, costmap, cp, N, num_controllers=B, seed=5) as ctx:
+        full = ctx.compute_control(states, U)
+    for fused in (1, 0):
+        halves = []
+        for k in range(2):
+            sl = slice(k * B // 2, (k + 1) * B // 2)
+            with make_context("nn", models, costmap, cp, N, num_controllers=B // 2, controller_begin=k * B // 2, seed=5,
+                              variant=10) as ctx:
+                ctx.set_fused_noise(fused)
+                halves.append(ctx.compute_control(states[sl], U[sl]))
+        for key in ("U", "normalizer", "baseline"):
+            np.testing.assert_array_equal(np.concatenate([h[key] for h in halves]), full[key])
+
+
+def test_bf_batched_controllers_match_oracle(models, costmap):
+    """Basis-function dynamics in batched mode (B controllers x 256 rollouts)."""
+    from autorally_b200.params import ellipse_states
+    cp = cost_params_for(costmap, desired_speed=6.0)
+    B, N, T = 16, 256, 100
+    states = ellipse_states(B)
+    eps = np.random.default_rng(29).standard_normal((B, N, T, 2)).astype(np.float32)
+    U = np.broadcast_to(warm_controls(T), (B, T, 2)).copy()
+    with make_context("bf", models, costmap, cp, N, num_controllers=B) as ctx:
+        ctx.set_noise(eps)
+        got = ctx.compute_control(states, U)
+        costs, V = ctx.rollout_costs(), ctx.sampled_controls()
+    o = make_oracle("bf", models, costmap, cp)
+    for b in range(B):
+        want = o.compute_control(states[b], U[b], np.zeros(4), NU, eps[b][None], threads=8)
+        np.testing.assert_array_equal(V[b], want["V"])
+        check_costs(costs[b], want["costs"], T, cost_tol=2e-4, min_ok=0.98)
+        assert rel_err(got["U"][b], want["U"]).max() < 2e-4
+        assert rel_err(got["state_solution"][b], want["state_solution"]).max() < 2e-4
+
+
+def test_bf_sharded_rollouts_reproduce_unsharded_answer(models, costmap):
+    """Basis-function dynamics with the rollouts sharded 4 ways (SURVEY section 8e on one GPU) = the unsharded controller;
+    both against the oracle."""
+    import torch
+    cp = cost_params_for(costmap, desired_speed=6.0)
+    N, T, G = 2560, 100, 4
+    eps = np.random.default_rng(31).standard_normal((N, T, 2)).astype(np.float32)
+    state, U = top_state(4.0), straight_controls(T)
+    with make_context("bf", models, costmap, cp, N) as ctx:
+        ctx.set_noise(eps)
+        want = ctx.compute_control(state, U)
+    ora = make_oracle("bf", models, costmap, cp).compute_control(state, U, np.zeros(4), NU, eps[None], threads=8)
+    assert rel_err(want["U"], ora["U"]).max() < 2e-4
+    per = N // G
+    shards = []
+    for g in range(G):
+        ctx = make_context("bf", models, costmap, cp, N, rollout_begin=g * per, rollout_count=per)
+        ctx.set_noise(eps[g * per:(g + 1) * per])
+        ctx.shard_begin(state, U)
+        shards.append(ctx)
+    sf = shards[0].shard_floats()
+    gathered = torch.empty((G, 1, sf), dtype=torch.float32, device="cuda")
+    for g, ctx in enumerate(shards):
+        gathered[g, 0].copy_(ctypes_float_array(ctx.shard_partials_ptr(), sf))
+    torch.cuda.synchronize()
+    for ctx in shards:
+        got = ctx.shard_finish(gathered.data_ptr(), G)
+        assert rel_err(got["U"], want["U"]).max() < 1e-5
+        assert rel_err(got["normalizer"], want["normalizer"]).max() < 1e-5
+        assert got["baseline"] == want["baseline"]
+        ctx.close()
+
+
+@pytest.mark.parametrize("variant", [9, 10])
+def test_multiple_iterations_on_the_default_kernels(models, costmap, variant):
+    """num_iters > 1 (PI/mppi_controller.cu:609) on the half-warp latency kernel and the tensor-core kernel."""
+    cp = cost_params_for(costmap)
+    N, T, iters = 1920, 100, 3
+    eps = np.random.default_rng(41).standard_normal((iters, N, T, 2)).astype(np.float32)
+    state, U = top_state(4.0), straight_controls(T)
+    want = make_oracle("nn", models, costmap, cp).compute_control(state, U, np.zeros(4), NU, eps, threads=8)
+    with make_context("nn", models, costmap, cp, N, num_iters=iters, variant=variant) as ctx:
+        ctx.set_noise(eps)
+        got = ctx.compute_control(state, U)
+        assert ctx.resolved_variant() == variant
+    assert rel_err(got["U"], want["U"]).max() < 2e-4
+    assert rel_err(got["state_solution"], want["state_solution"]).max() < 2e-4
+    check_scalars(got, want, 5e-4)   # three chained iterations: the last one starts from a U that already differs by ~1e-6
+
+
+# ---- any NeuralNetModel<7,2,3,6,...,4> layer pack: the run-time layer kernel (MPPI_ROLLOUT_GENERIC = 11) ----
+
+@pytest.mark.parametrize("structure", [(6, 16, 16, 4), (6, 48, 4), (6, 4), (6, 20, 33, 7, 4), (6, 128, 128, 4), (6, 100, 4)])
+def test_arbitrary_layer_packs_match_oracle(models, costmap, structure):
+    """PI/neural_net_model.cuh:48-52 takes any layer pack; mppi_set_nn_params accepts widths <= 128 at any depth <= 16."""
+    cp = cost_params_for(costmap)
+    theta, st = random_network(structure, seed=sum(structure))
+    N, T = 1920, 100
+    eps = np.random.default_rng(43).standard_normal((1, N, T, 2)).astype(np.float32)
+    state, U = top_state(4.0), straight_controls(T)
+    hist = np.array([0.1, 0.3, 0.11, 0.32], np.float32)
+    want = make_oracle("nn", models, costmap, cp, theta=theta, structure=st).compute_control(state, U, hist, NU, eps, threads=8)
+    with make_context("nn", models, costmap, cp, N, theta=theta, structure=st) as ctx:
+        assert ctx.resolved_variant() == 11
+        ctx.set_noise(eps)
+        got = ctx.compute_control(state, U, hist)
+        got["costs"], got["crash"], got["V"] = ctx.rollout_costs(), ctx.rollout_crash(), ctx.sampled_controls()
+        got["U_new"], got["launches"] = ctx.unsmoothed_controls(), ctx.last_launch_count()
+    check_pair(want, got, cost_tol=2e-4 if max(structure) > 64 else 1e-4)
+
+
+@pytest.mark.parametrize("N,T", [(64, 1), (192, 33), (1920, 100), (4096, 70)])
+def test_run_time_layer_kernel_on_the_shipped_network(models, costmap, N, T):
+    """The run-time layer kernel selected explicitly for NeuralNetModel<7,2,3,6,32,32,4>: same oracle, ragged sizes."""
+    want, got = run_pair("nn", models, costmap, N, T=T, seed=N + T, variant=11)
+    check_pair(want, got)
+
+
+def test_run_time_layer_kernel_batched_and_sharded(models, costmap):
+    from autorally_b200.params import ellipse_states
+    cp = cost_params_for(costmap)
+    theta, st = random_network((6, 24, 24, 4), seed=3)
+    B, N, T = 8, 256, 100
+    states = ellipse_states(B)
+    eps = np.random.default_rng(47).standard_normal((B, N, T, 2)).astype(np.float32)
+    U = np.broadcast_to(warm_controls(T), (B, T, 2)).copy()
+    with make_context("nn", models, costmap, cp, N, num_controllers=B, theta=theta, structure=st) as ctx:
+        ctx.set_noise(eps)
+        got = ctx.compute_control(states, U)
+        costs = ctx.rollout_costs()
+    o = make_oracle("nn", models, costmap, cp, theta=theta, structure=st)
+    for b in range(B):
+        want = o.compute_control(states[b], U[b], np.zeros(4), NU, eps[b][None], threads=8)
+        check_costs(costs[b], want["costs"], T, min_ok=0.98)
+        assert rel_err(got["U"][b], want["U"]).max() < 1e-4
+    # rollout shard [128, 256) of a 256-rollout controller: global indices drive the bookkeeping
+    with make_context("nn", models, costmap, cp, N, rollout_begin=128, rollout_count=128, theta=theta, structure=st) as ctx:
+        ctx.set_noise(eps[0, 128:])
+        ctx.shard_begin(states[0], U[0])
+        V = ctx.sampled_controls()
+    want = o.compute_control(states[0], U[0], np.zeros(4), NU, eps[0][None], threads=8)
+    np.testing.assert_array_equal(V, want["V"][128:])
+
+
+def test_unsupported_layer_packs_are_refused(models, costmap):
+    from autorally_b200.capi import MppiError
+    cp = cost_params_for(costmap)
+    for structure, code in (((6, 129, 4), -2), ((5, 32, 4), -1), ((6, 32, 5), -1)):
+        theta, st = random_network(structure)
+        with pytest.raises(MppiError) as ei:
+            make_context("nn", models, costmap, cp, 256, theta=theta, structure=st)
+        assert ei.value.code == code

@@ -11,8 +11,9 @@ import numpy as np
 import pytest
 
 from oracle import reference as ref
-from tests.common import cost_params_for, default_state, make_context, make_oracle, straight_controls, top_state, warm_controls
-from tests.test_parity_gpu import check_costs, rel_err
+from tests.common import (cost_params_for, default_state, make_context, make_oracle, random_network, straight_controls, top_state,
+                          warm_controls)
+from tests.test_parity_gpu import TRUE_REL_BOUND, check_costs, rel_err, true_rel_err
 
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libautorally_ref.so not built")]
 
@@ -33,10 +34,14 @@ def compare(got, want, T, what, cost_tol=1e-4, u_tol=1e-4):
     np.testing.assert_array_equal(got["V"], want["V"], err_msg=what + ": sampled-control bookkeeping")
     check_costs(got["costs"], want["costs"], T, cost_tol)
     assert abs(got["costs"].min() - want["costs"].min()) <= cost_tol * (1 + abs(want["costs"].min())), what
-    assert rel_err(got["normalizer"], want["normalizer"]) < 1e-3, what
-    assert rel_err(got["trajectory_cost"], want["trajectory_cost"]) < 1e-3, what
+    for k in ("normalizer", "trajectory_cost"):   # truly relative (PI/mppi_controller.cu:641-652)
+        g, w = float(got[k]), float(want[k])
+        assert abs(g - w) <= cost_tol * abs(w), "%s: %s got %.9g want %.9g" % (what, k, g, w)
     e = rel_err(got["U"], want["U"]).max()
     assert e < u_tol, "%s: max control rel err %.3g" % (what, e)
+    tr = true_rel_err(got["U"], want["U"])   # reported; see tests/test_parity_gpu.py:TRUE_REL_BOUND for why it is not held to 1e-4
+    print("%s: max |dU| / (1 + |U|) = %.3g, true relative over |u| > 1e-2 = %.3g" % (what, e, tr))
+    assert tr < TRUE_REL_BOUND, "%s: true relative control error %.3g over |u| > 1e-2" % (what, tr)
     assert rel_err(got["state_solution"], want["state_solution"]).max() < 1e-4, what
     assert rel_err(got["control_solution"], want["control_solution"]).max() < u_tol, what
 
@@ -74,7 +79,7 @@ def test_nn_spread_weights_three_way(models, costmap, gamma):
     state, U = top_state(4.0), straight_controls(100)
     want = reference_run(ref.REF_NN_1920, models["autorally_nnet_theta"], costmap, cp, state, U, gamma=gamma)
     assert want["normalizer"] > (15 if gamma > 0.1 else 150)
-    for variant in (2, 7, 9, 10):
+    for variant in (2, 9, 10):
         got = cuda_run("nn", models, costmap, cp, 1920, state, U, want["eps"], gamma=gamma, variant=variant)
         compare(got, want, 100, "cuda (variant %d) vs reference" % variant)
     o = make_oracle("nn", models, costmap, cp).compute_control(state, U, HIST, NU, want["eps"], gamma=gamma, threads=8)
@@ -209,3 +214,80 @@ def test_wider_deeper_network_three_way(models, costmap):
         compare(got, want, 100, "cuda (variant %d) vs reference, 64-wide network" % variant, cost_tol=3e-4)
     o = make_oracle("nn", models, costmap, cp, tag="wider_deeper", negate_yaw_der=False).compute_control(state, U, HIST, NU, want["eps"], threads=8)
     compare(o, want, 100, "oracle vs reference, 64-wide network", cost_tol=3e-4)
+
+
+@pytest.mark.parametrize("stride", [1, 3])
+def test_slide_with_stride_three_way(models, costmap, stride):
+    """slideControlAndStateSeq(stride) (PI/mppi_controller.cu:527-568), including the stride != 1 branch that fills
+    control_hist_ from the flat U_ at index stride - 2: the reference's own slide against the oracle's and the drop-in
+    C++ template's (tests/cpp/host_cpu_driver.cpp `slide`), then a computeControl from the slid sequences with
+    optimization_stride = stride on all three."""
+    import os
+    import subprocess
+    from oracle.oracle import Oracle
+    from tests.test_host_cpp import cpu_driver
+    cp = cost_params_for(costmap)
+    state, init_u = top_state(4.0), (0.05, -0.01)
+    o = make_oracle("nn", models, costmap, cp)
+    with ref.ReferenceController(ref.REF_NN_1920, models["autorally_nnet_theta"], costmap, cp, init_u=init_u, optimization_stride=stride) as rc, \
+            make_context("nn", models, costmap, cp, 1920, optimization_stride=stride) as ctx:
+        rc.set_controls(warm_controls(100), HIST)
+        first = rc.compute_control(state)
+        U0, hist0 = rc.get_controls()
+        rc.slide(stride)
+        U_ref, hist_ref = rc.get_controls()
+        U_sl, hist_sl = Oracle.slide_control_seq(U0, hist0, init_u, stride)
+        np.testing.assert_array_equal(U_sl, U_ref)
+        np.testing.assert_array_equal(hist_sl, hist_ref)
+        # the drop-in MPPIController template's slide (host C++, no GPU involved)
+        out = subprocess.check_output([cpu_driver(), "slide", str(stride), repr(float(init_u[0])), repr(float(init_u[1]))] +
+                                      [repr(float(v)) for v in hist0] + [repr(float(v)) for v in U0.reshape(-1)], text=True).split()
+        tmpl = np.array([float(v) for v in out], np.float32)
+        np.testing.assert_array_equal(tmpl[:4], hist_ref)
+        np.testing.assert_array_equal(tmpl[4:].reshape(100, 2), U_ref)
+        # plan again from the slid sequence (the predicted state = head of the slid state sequence)
+        state2 = first["state_solution"][stride]
+        want = rc.compute_control(state2)
+        want["costs"], want["V"] = rc.rollout_costs(state2, U_ref, want["eps"][0])
+        ctx.set_noise(want["eps"])
+        got = ctx.compute_control(state2, U_ref, hist_ref)
+        got["costs"], got["V"] = ctx.rollout_costs(), ctx.sampled_controls()
+        compare(got, want, 100, "cuda vs reference after slide(%d)" % stride)
+        oo = o.compute_control(state2, U_ref, hist_ref, NU, want["eps"], opt_delay=stride, threads=8)
+        compare(oo, want, 100, "oracle vs reference after slide(%d)" % stride)
+
+
+@pytest.mark.parametrize("kind,structure", [(ref.REF_NN16_1920, (6, 16, 16, 4)), (ref.REF_NN48_1920, (6, 48, 4))])
+def test_arbitrary_layer_packs_three_way(models, costmap, kind, structure):
+    """Layer packs without a dedicated kernel -- NeuralNetModel<7,2,3,6,16,16,4> and <7,2,3,6,48,4>, instantiated from the
+    reference's variadic template in oracle/ref_harness.cu, random weights -- on the run-time layer kernel
+    (rollout_generic.cu, finalize_kernel<0>) and the CPU oracle, against the reference's own kernels."""
+    cp = cost_params_for(costmap)
+    theta, st = random_network(structure, seed=17)
+    state, U = top_state(4.0), straight_controls(100)
+    with ref.ReferenceController(kind, theta, costmap, cp) as rc:
+        rc.set_controls(U, HIST)
+        want = rc.compute_control(state)
+        want["costs"], want["V"] = rc.rollout_costs(state, U, want["eps"][0])
+    with make_context("nn", models, costmap, cp, 1920, theta=theta, structure=st) as ctx:
+        assert ctx.resolved_variant() == 11
+        ctx.set_noise(want["eps"])
+        got = ctx.compute_control(state, U, HIST)
+        got["costs"], got["V"] = ctx.rollout_costs(), ctx.sampled_controls()
+    compare(got, want, 100, "cuda (run-time layer kernel) vs reference %s" % (structure,))
+    o = make_oracle("nn", models, costmap, cp, theta=theta, structure=st).compute_control(state, U, HIST, NU, want["eps"], threads=8)
+    compare(o, want, 100, "oracle vs reference %s" % (structure,))
+
+
+def test_reference_kernel_times_are_reported(models, costmap):
+    """Device time of the reference's own kernels on this GPU (bench.py --impl reference reports the same split)."""
+    cp = cost_params_for(costmap)
+    with ref.ReferenceController(ref.REF_NN_1920, models["autorally_nnet_theta"], costmap, cp) as rc:
+        rc.set_controls(straight_controls(100), HIST)
+        k = rc.time_kernels(top_state(4.0), reps=10)
+        e2e = rc.time_compute_control(top_state(4.0), reps=10)
+        want = rc.compute_control(top_state(4.0))   # the twin generator is still in step with the controller's
+        costs, V = rc.rollout_costs(top_state(4.0), straight_controls(100), want["eps"][0])
+    print("reference kernels (ms): %s; computeControl %.3f ms" % (k, e2e))
+    assert all(v > 0 for v in k.values()) and sum(k.values()) < e2e
+    np.testing.assert_array_equal(V[7, 1:], (straight_controls(100)[1:] + want["eps"][0, 7, 1:] * NU).astype(np.float32))
