@@ -180,7 +180,11 @@ bool supports_fused_noise(const mppi_ctx *c) {
 }
 bool fused_noise_now(const mppi_ctx *c) {
   if (c->injected || c->fused_mode == 0 || !supports_fused_noise(c)) return false;
-  return true;  // automatic = in place wherever the kernel supports it (no sampler launch, no noise round trip through HBM)
+  // automatic: in place for the network kernels (no sampler launch, no noise round trip through HBM; 1M rollouts 3.89 ->
+  // 3.86 ms per step), the sampler kernel for the basis-function kernel, whose transcendental chain does not hide the
+  // Philox rounds (1M rollouts: 2.63 ms with the sampler kernel, 2.79 ms in place; profiles/exp_fused_r02.txt)
+  if (c->fused_mode < 0 && c->cfg.dynamics == MPPI_DYNAMICS_BF) return false;
+  return true;
 }
 
 cudaError_t launch_rollout(mppi_ctx *c) {
