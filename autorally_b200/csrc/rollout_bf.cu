@@ -39,7 +39,7 @@ __device__ __forceinline__ bool wait_at_least(volatile int *counter, int want, v
 
 __global__ void __launch_bounds__(64) rollout_bf_split_kernel(const __grid_constant__ RolloutParams p) {
   __shared__ BfRing ring;
-  __shared__ float sw[100];
+  __shared__ __align__(16) float sw[100];
   const int tid = threadIdx.x, lane = tid & 31, role = tid >> 5;
   for (int i = tid; i < 100; i += 64) sw[i] = p.theta_t[i];
   if (tid == 0) { ring.produced = 0; ring.consumed = 0; ring.failed = 0; }

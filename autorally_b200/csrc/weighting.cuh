@@ -260,7 +260,7 @@ struct FinalizeParams {
   int is_nn64;  // 6-64-64-64-64-4 with 256 threads: CtaMlp<64, 4> (weights in registers)
   float *inbox;           // [B][inbox_stride]  (U is rewritten for the next iteration / resident step)
   float *outbox;          // [B][outbox_stride]: result[4] | U_smoothed[2T] | U_new[2T] | state_sol[7T] | ctrl_sol[2T]
-  const float *theta_t;   // NN: transposed packed weights; BF: theta 4x25
+  const float *theta_t;   // NN: transposed packed weights; BF: theta transposed [25][4]
   const int *net_structure;
   int num_layers;         // NN: entries of net_structure; 0 = basis-function model
   int is_nn32;            // the 6-32-32-4 network: nominal trajectory on the WarpMlp32 fast path

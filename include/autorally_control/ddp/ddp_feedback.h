@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <limits>
 #include <type_traits>
 #include <utility>
 #include <vector>
@@ -59,13 +60,17 @@ struct ModelWrapperDDP {
       for (int c = 0; c < StateSize + ControlSize; c++) j(r, c) = model_->jac_(r, c);
     return j;
   }
-  Jacobian df_impl(const State &x, const Control &u, long) {  // central differences (DDP/ddp_dynamics.h:75-79)
+  // Central differences with the step rule of Eigen::NumericalDiff<..., Central>, which the reference uses for models
+  // without computeGrad (DDP/ddp_dynamics.h:75-79): h = sqrt(epsilon) |v|, or sqrt(epsilon) when v == 0.
+  Jacobian df_impl(const State &x, const Control &u, long) {
     Jacobian j;
+    const float eps = std::sqrt(std::numeric_limits<float>::epsilon());
     for (int c = 0; c < StateSize + ControlSize; c++) {
       State xp = x, xm = x;
       Control up = u, um = u;
       const float v = c < StateSize ? x(c) : u(c - StateSize);
-      const float h = 1e-3f * std::max(1.0f, std::fabs(v));
+      float h = eps * std::fabs(v);
+      if (h == 0.0f) h = eps;
       if (c < StateSize) { xp(c) += h; xm(c) -= h; } else { up(c - StateSize) += h; um(c - StateSize) -= h; }
       const State fp = f(xp, up), fm = f(xm, um);
       for (int r = 0; r < StateSize; r++) j(r, c) = (fp(r) - fm(r)) / (2.0f * h);

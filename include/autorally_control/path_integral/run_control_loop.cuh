@@ -27,6 +27,22 @@
 
 namespace autorally_control {
 
+// Optional plant hooks (sim_plant.h has them, a plant modelled on AutorallyPlant need not): injected noise and an arbitration log.
+template <class P, class C>
+auto loop_inject_noise(P *robot, C *a, C *b, int iteration, int) -> decltype(robot->hasInjectedNoise(0), void()) {
+  if (!robot->hasInjectedNoise(iteration)) return;
+  a->setNoise(robot->injectedNoise(iteration), robot->injectedNoiseCount());
+  b->setNoise(robot->injectedNoise(iteration), robot->injectedNoiseCount());
+}
+template <class P, class C>
+void loop_inject_noise(P *, C *, C *, int, long) {}
+template <class P, class C, class G>
+auto loop_log_arbitration(P *robot, C *a, C *b, const G &gains, int T, int) -> decltype(robot->trajectoryCosts(), void()) {
+  robot->logArbitration(a->getComputedTrajectoryCost(), b->getComputedTrajectoryCost(), a->getControlSequenceU(), b->getControlSequenceU(), gains, T);
+}
+template <class P, class C, class G>
+void loop_log_arbitration(P *, C *, C *, const G &, int, long) {}
+
 template <class CONTROLLER_T, class PLANT_T>
 void runControlLoop(CONTROLLER_T *predicted_state_controller, CONTROLLER_T *actual_state_controller, PLANT_T *robot,
                     std::map<std::string, XmlRpc::XmlRpcValue> *params, std::atomic<bool> *is_alive) {
@@ -105,6 +121,7 @@ void runControlLoop(CONTROLLER_T *predicted_state_controller, CONTROLLER_T *actu
       actual_state_controller->slideControlAndStateSeq(stride);
       predicted_state_controller->slideControlAndStateSeq(stride);
     }
+    loop_inject_noise(robot, actual_state_controller, predicted_state_controller, num_iter - 1, 0);
     // the hot path, twice (:218-219).  The two plans are independent, so both are enqueued before either is awaited:
     // each fills a few percent of a B200 and they overlap on the device.
     actual_state_controller->computeControlAsync(fixed());
@@ -137,6 +154,7 @@ void runControlLoop(CONTROLLER_T *predicted_state_controller, CONTROLLER_T *actu
       state_solution = predicted_state_controller->getStateSeq();
       feedback_gain = predicted_state_controller->getFeedbackGains().feedback_gain;
     }
+    loop_log_arbitration(robot, actual_state_controller, predicted_state_controller, feedback_gain, num_timesteps, 0);
     robot->setSolution(state_solution, control_solution, feedback_gain, last_pose_update, avg_loop_ms, to_use);
     status = robot->checkStatus();
     if (status != 0 && debug_mode) {  // the host model is the plant (:296-302)

@@ -42,6 +42,27 @@ class SimPlant {
     executed_controls_.insert(executed_controls_.end(), control_seq.begin(), control_seq.begin() + 2);
     controller_used_.push_back(used == ControllerType::ACTUAL_STATE ? 0 : 1);
   }
+  /// Test hooks (no counterpart in the reference): per-iteration N(0,1) draws to inject into BOTH controllers -- the
+  /// reference's two controllers each seed cuRAND with 1234 and therefore draw the same sequence -- and a log of what the
+  /// arbitration saw and handed over.
+  bool hasInjectedNoise(int iteration) const { return noise_per_iter_ > 0 && (size_t)(iteration + 1) * noise_per_iter_ <= noise_.size(); }
+  const float *injectedNoise(int iteration) const { return noise_.data() + (size_t)iteration * noise_per_iter_; }
+  size_t injectedNoiseCount() const { return noise_per_iter_; }
+  void setInjectedNoise(std::vector<float> noise, size_t per_iteration) { noise_ = std::move(noise); noise_per_iter_ = per_iteration; }
+  template <class GAINS>
+  void logArbitration(float cost_actual, float cost_predicted, const std::vector<float> &u_actual, const std::vector<float> &u_predicted,
+                      const GAINS &gains, int timesteps) {
+    trajectory_costs_.push_back(cost_actual); trajectory_costs_.push_back(cost_predicted);
+    u_actual_.insert(u_actual_.end(), u_actual.begin(), u_actual.end());
+    u_predicted_.insert(u_predicted_.end(), u_predicted.begin(), u_predicted.end());
+    for (int k = 0; k < timesteps; k++)
+      for (int a = 0; a < 2; a++)
+        for (int b = 0; b < 7; b++) gains_.push_back(k < (int)gains.size() ? gains[k](a, b) : 0.0f);
+  }
+  const std::vector<float> &trajectoryCosts() const { return trajectory_costs_; }  // [iterations][2]: actual, predicted
+  const std::vector<float> &loggedGains() const { return gains_; }                // [iterations][T][2][7]
+  const std::vector<float> &loggedUActual() const { return u_actual_; }
+  const std::vector<float> &loggedUPredicted() const { return u_predicted_; }
   /// 1 = "no pose updates: integrate the model" -- the reference's status for debug mode (PI/run_control_loop.cuh:296)
   int checkStatus() const { return 1; }
   template <class IMG> void setDebugImage(const IMG &) {}
@@ -66,6 +87,8 @@ class SimPlant {
   PathIntegralParamsConfig dcfg_;
   std::vector<int> model_description_, controller_used_;
   std::vector<float> model_data_, state_seq_, control_seq_, executed_states_, executed_controls_;
+  std::vector<float> noise_, trajectory_costs_, gains_, u_actual_, u_predicted_;
+  size_t noise_per_iter_ = 0;
 };
 
 }  // namespace autorally_control

@@ -10,8 +10,12 @@
 //     (PI/mppi_controller.{cuh,cu}, PI/neural_net_model.{cuh,cu}, PI/generalized_linear.{cuh,cu}, PI/car_bfs.cuh,
 //     PI/car_kinematics.cuh, PI/costs.{cuh,cu}), built for sm_100a instead of sm_52 and without -maxrregcount=32;
 //     cuRAND (XORWOW, seed 1234) is the toolkit's own library.
-//   * stand-ins (oracle/ref_shim/): Eigen, cnpy, ROS/XmlRpc, OpenCV, Boost and the DDP headers, none of which is
-//     installed here.  They only carry host-side containers and plain float loops; no device code uses them.
+//   * also the reference's, unmodified: DDP<...>::run with TrackingCostDDP / ModelWrapperDDP (DDP/*.h) behind
+//     computeFeedbackGains, and runControlLoop (PI/run_control_loop.cuh) with its two-controller arbitration;
+//   * stand-ins (oracle/ref_shim/): Eigen, cnpy, ROS/XmlRpc (+ message headers), OpenCV and Boost, none of which is
+//     installed here.  They only carry host-side containers and plain float loops; no device code uses them.  The plant
+//     runControlLoop drives is declared by the reference's PI/autorally_plant.h; its ROS implementation
+//     (SRC/autorally_plant.cpp) is replaced below by a recording stand-in (debug mode: the loop itself integrates the model).
 // The harness reaches private members the way the reference's own tests do (`#define private public`,
 // autorally_core/test/serialSensorInterfaceTest.cpp:43-61).
 #include <cfloat>
@@ -44,6 +48,7 @@
 #include <autorally_control/path_integral/car_kinematics.cuh>
 #include <autorally_control/path_integral/generalized_linear.cuh>
 #include <autorally_control/path_integral/mppi_controller.cuh>
+#include <autorally_control/path_integral/run_control_loop.cuh>   // + PI/autorally_plant.h (class declaration only)
 #undef private
 #undef protected
 
@@ -60,6 +65,71 @@ typedef struct ref_cost_params {
 } ref_cost_params;
 }
 
+// ---- recording stand-in for the member functions of AutorallyPlant that runControlLoop calls (declared by the reference's
+//      PI/autorally_plant.h:94-300; the ROS node of SRC/autorally_plant.cpp is not built) ----
+namespace {
+struct LoopRecorder {
+  int T = 0, N = 0;
+  size_t noise_per_iter = 0;
+  std::vector<float> states, controls, tcost, gains, eps, u_actual, u_predicted;   // per iteration
+  std::vector<int> used;
+  // filled by RefImpl::run_loop: how to read the two controllers after each iteration
+  float (*traj_cost)(void *) = nullptr;
+  const std::vector<float> *(*controls_of)(void *) = nullptr;
+  void *actual = nullptr, *predicted = nullptr;
+  curandGenerator_t twin = nullptr;
+  float *eps_d = nullptr;
+};
+LoopRecorder *g_rec = nullptr;
+}  // namespace
+
+namespace autorally_control {
+AutorallyPlant::AutorallyPlant(ros::NodeHandle, ros::NodeHandle, std::map<std::string, XmlRpc::XmlRpcValue> *params, bool nodelet)
+    : new_model_available_(false), is_nodelet_(nodelet), status_(1), debug_mode_(true), activated_(true) {
+  std::memset(&full_state_, 0, sizeof(full_state_));
+  full_state_.x_pos = (float)(double)(*params)["x_pos"];
+  full_state_.y_pos = (float)(double)(*params)["y_pos"];
+  full_state_.yaw = (float)(double)(*params)["heading"];
+  full_state_.q0 = 1.0f;
+  hz_ = (int)(*params)["hz"];
+  numTimesteps_ = (int)(*params)["num_timesteps"];
+}
+AutorallyPlant::FullState AutorallyPlant::getState() { return full_state_; }
+ros::Time AutorallyPlant::getLastPoseTime() { return last_pose_call_; }
+void AutorallyPlant::setTimingInfo(double, double, double) {}
+bool AutorallyPlant::hasNewDynRcfg() { return false; }
+autorally_control::PathIntegralParamsConfig AutorallyPlant::getDynRcfgParams() { return costParams_; }
+bool AutorallyPlant::hasNewModel() { return false; }
+void AutorallyPlant::getModel(std::vector<int> &, std::vector<float> &) {}
+void AutorallyPlant::modelCall(autorally_msgs::neuralNetModel) {}
+void AutorallyPlant::setDebugImage(cv::Mat) {}
+int AutorallyPlant::checkStatus() { return 1; }  // "no pose updates": with debug_mode the loop integrates the model (PI/run_control_loop.cuh:296)
+void AutorallyPlant::displayDebugImage(const ros::TimerEvent &) {}
+void AutorallyPlant::shutdown() {}
+void AutorallyPlant::setSolution(std::vector<float> traj, std::vector<float> controls, util::EigenAlignedVector<float, 2, 7> gains,
+                                 ros::Time, double, ControllerType used) {
+  LoopRecorder *r = g_rec;
+  if (!r) return;
+  r->states.insert(r->states.end(), traj.begin(), traj.begin() + 7);
+  r->controls.insert(r->controls.end(), controls.begin(), controls.begin() + 2);
+  r->used.push_back(used == ControllerType::ACTUAL_STATE ? 0 : 1);
+  r->tcost.push_back(r->traj_cost(r->actual));
+  r->tcost.push_back(r->traj_cost(r->predicted));
+  const std::vector<float> *ua = r->controls_of(r->actual), *up = r->controls_of(r->predicted);
+  r->u_actual.insert(r->u_actual.end(), ua->begin(), ua->end());
+  r->u_predicted.insert(r->u_predicted.end(), up->begin(), up->end());
+  for (int k = 0; k < r->T; k++)
+    for (int a = 0; a < 2; a++)
+      for (int b = 0; b < 7; b++) r->gains.push_back(k < (int)gains.size() ? gains[k](a, b) : 0.0f);
+  // the draws both controllers consumed in this iteration: each owns a cuRAND generator seeded 1234 (PI/mppi_controller.cu:330-331)
+  // and makes one curandGenerateNormal call per computeControl, so the two draw the SAME sequence; the twin replays it
+  curandGenerateNormal(r->twin, r->eps_d, r->noise_per_iter, 0.0f, 1.0f);
+  const size_t off = r->eps.size();
+  r->eps.resize(off + r->noise_per_iter);
+  cudaMemcpy(r->eps.data() + off, r->eps_d, r->noise_per_iter * sizeof(float), cudaMemcpyDeviceToHost);
+}
+}  // namespace autorally_control
+
 namespace {
 
 struct RefBase {
@@ -72,6 +142,8 @@ struct RefBase {
   virtual int rollout_costs(const float *state, const float *U, const float *eps, float *costs, float *V) = 0;
   virtual int time_compute(const float *state, int reps, float *ms_per_call) = 0;
   virtual int time_kernels(const float *state, int reps, float *ms4) = 0;
+  virtual int feedback_gains(const float *state, float *gains, float *feedforward) = 0;
+  virtual int run_loop(const float *pose3, int iterations, int use_feedback_gains, LoopRecorder *rec) = 0;
 };
 
 typedef NeuralNetModel<7, 2, 3, 6, 32, 32, 4> RefNN;
@@ -109,6 +181,7 @@ struct RefImpl : RefBase {
   int init_common(const float *lo_hi, const float *costmap, int w, int h, const ref_cost_params *cp, const float *nu,
                   const float *init_u, int hz, int T_, int opt_stride_, float gamma, int num_iters) {
     T = T_; iters = num_iters; opt_stride = opt_stride_;
+    nu_saved[0] = nu[0]; nu_saved[1] = nu[1]; init_u_saved[0] = init_u[0]; init_u_saved[1] = init_u[1]; gamma_saved = gamma; hz_saved = hz;
     costs = new MPPICosts(w, h);
     costs->costmap_tex_ = 0;  // uninitialised in the reference; destroyed by the first costmapToTexture (PI/costs.cu:152)
     costs->l1_cost_ = cp->l1_cost != 0;  // uninitialised by the (w, h) constructor (PI/costs.cu:41-50)
@@ -186,6 +259,65 @@ struct RefImpl : RefBase {
 
   // Wall-clock of the reference's computeControl on this GPU (its own host syncs and memcpys included).
   int time_kernels(const float *state, int reps, float *ms4) override;
+
+  // computeFeedbackGains (PI/mppi_controller.cu:425-437) -> DDP<ModelWrapperDDP<MODEL>>::run (DDP/ddp.h:49-157) around the
+  // controller's current state / control solution; gains [T][2][7], feedforward [T][2]
+  int feedback_gains(const float *state, float *gains, float *feedforward) override {
+    Eigen::MatrixXf s(7, 1);
+    for (int i = 0; i < 7; i++) s(i) = state[i];
+    ctrl->computeFeedbackGains(s);
+    auto res = ctrl->getFeedbackGains();
+    for (int k = 0; k < T; k++)
+      for (int a = 0; a < 2; a++) {
+        for (int b = 0; b < 7; b++) gains[(k * 2 + a) * 7 + b] = k < (int)res.feedback_gain.size() ? res.feedback_gain[k](a, b) : 0.0f;
+        if (feedforward) feedforward[k * 2 + a] = res.feedforward_gain(a, k);
+      }
+    return 0;
+  }
+
+  // The reference's runControlLoop (PI/run_control_loop.cuh:84-321), unmodified, in debug mode on two fresh controllers that
+  // share this model and cost object (SRC/path_integral_main.cu:119-122), for `iterations` iterations.
+  float nu_saved[2] = {0, 0}, init_u_saved[2] = {0, 0}, gamma_saved = 0;
+  int hz_saved = 50;
+  static float traj_cost_of(void *c) { return static_cast<Controller *>(c)->getComputedTrajectoryCost(); }
+  static const std::vector<float> *controls_of(void *c) { return &static_cast<Controller *>(c)->U_; }
+  int run_loop(const float *pose3, int iterations, int use_feedback_gains, LoopRecorder *rec) override {
+    std::map<std::string, XmlRpc::XmlRpcValue> params;
+    params["x_pos"] = XmlRpc::XmlRpcValue((double)pose3[0]);
+    params["y_pos"] = XmlRpc::XmlRpcValue((double)pose3[1]);
+    params["heading"] = XmlRpc::XmlRpcValue((double)pose3[2]);
+    params["hz"] = XmlRpc::XmlRpcValue(hz_saved);
+    params["optimization_stride"] = XmlRpc::XmlRpcValue(opt_stride);
+    params["num_timesteps"] = XmlRpc::XmlRpcValue(T);
+    params["use_feedback_gains"] = XmlRpc::XmlRpcValue(use_feedback_gains != 0);
+    params["debug_mode"] = XmlRpc::XmlRpcValue(true);
+    params["use_only_actual_state_controller"] = XmlRpc::XmlRpcValue(false);
+    params["use_only_predicted_state_controller"] = XmlRpc::XmlRpcValue(false);
+    params["profiler_max_iter"] = XmlRpc::XmlRpcValue(iterations);
+    Controller *actual = new Controller(model, costs, nu_saved, init_u_saved, hz_saved, T, opt_stride, gamma_saved, iters, 0);
+    Controller *predicted = new Controller(model, costs, nu_saved, init_u_saved, hz_saved, T, opt_stride, gamma_saved, iters, 0);
+    ros::NodeHandle nh;
+    AutorallyPlant robot(nh, &params);
+    rec->T = T; rec->N = N; rec->noise_per_iter = (size_t)N * T * 2;
+    rec->traj_cost = &traj_cost_of; rec->controls_of = &controls_of; rec->actual = actual; rec->predicted = predicted;
+    curandCreateGenerator(&rec->twin, CURAND_RNG_PSEUDO_DEFAULT);
+    curandSetPseudoRandomGeneratorSeed(rec->twin, 1234ULL);
+    curandSetStream(rec->twin, 0);
+    cudaMalloc((void **)&rec->eps_d, rec->noise_per_iter * sizeof(float));
+    g_rec = rec;
+    std::atomic<bool> is_alive(true);
+    runControlLoop<Controller>(predicted, actual, &robot, &params, &is_alive);
+    g_rec = nullptr;
+    cudaError_t e = cudaDeviceSynchronize();
+    curandDestroyGenerator(rec->twin);
+    cudaFree(rec->eps_d);
+    for (Controller *c : {actual, predicted}) {
+      cudaFree(c->state_d_); cudaFree(c->nu_d_); cudaFree(c->traj_costs_d_); cudaFree(c->U_d_); cudaFree(c->du_d_);
+      curandDestroyGenerator(c->gen_);
+      delete c;
+    }
+    return e == cudaSuccess ? 0 : (int)e;
+  }
 
   int time_compute(const float *state, int reps, float *ms_per_call) override {
     Eigen::Matrix<float, 7, 1> s;
@@ -387,5 +519,25 @@ int ref_time_compute_control(void *h, const float *state, int reps, float *ms_pe
 }
 // ms4 = device time of {curandGenerateNormal, rolloutKernel, normExpKernel, weightedReductionKernel} per computeControl iteration
 int ref_time_kernels(void *h, const float *state, int reps, float *ms4) { return static_cast<RefBase *>(h)->time_kernels(state, reps, ms4); }
+// computeFeedbackGains around the controller's current solution (after ref_compute_control): gains [T][2][7], feedforward [T][2] or NULL
+int ref_feedback_gains(void *h, const float *state, float *gains, float *feedforward) {
+  return static_cast<RefBase *>(h)->feedback_gains(state, gains, feedforward);
+}
+// The reference's runControlLoop in debug mode (two controllers sharing model and costs) for `iterations` iterations from pose
+// (x, y, heading).  Per iteration: states [7] / controls [2] handed to the plant, controller_used (0 actual, 1 predicted), the two
+// controllers' trajectory costs [2], their control sequences [T][2], the gains handed over [T][2][7], and the N(0,1) draws both
+// controllers consumed [N][T][2].  Any output may be NULL.
+int ref_run_control_loop(void *h, const float *pose3, int iterations, int use_feedback_gains, float *states, float *controls, int *used,
+                         float *tcost, float *u_actual, float *u_predicted, float *gains, float *eps) {
+  LoopRecorder rec;
+  int rc = static_cast<RefBase *>(h)->run_loop(pose3, iterations, use_feedback_gains, &rec);
+  if (rc) return rc;
+  if ((int)rec.used.size() != iterations) return -7;
+  auto put = [](float *dst, const std::vector<float> &src) { if (dst) std::memcpy(dst, src.data(), src.size() * sizeof(float)); };
+  put(states, rec.states); put(controls, rec.controls); put(tcost, rec.tcost); put(u_actual, rec.u_actual);
+  put(u_predicted, rec.u_predicted); put(gains, rec.gains); put(eps, rec.eps);
+  if (used) std::memcpy(used, rec.used.data(), rec.used.size() * sizeof(int));
+  return 0;
+}
 
 }  // extern "C"

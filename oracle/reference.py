@@ -116,6 +116,31 @@ class ReferenceController:
             raise RuntimeError("ref_rollout_costs failed: %d" % rc)
         return costs, V
 
+    def feedback_gains(self, state):
+        """The reference's computeFeedbackGains(state) (DDP<...>::run, DDP/ddp.h:49-157) around the controller's current
+        solution (call compute_control first): gains [T, 2, 7] and feedforward terms [T, 2]."""
+        g, ff = np.zeros((self.T, 2, 7), np.float32), np.zeros((self.T, 2), np.float32)
+        rc = lib().ref_feedback_gains(self._h, _fp(_f32(state, 7)), _fp(g), _fp(ff))
+        if rc != 0:
+            raise RuntimeError("ref_feedback_gains failed: %d" % rc)
+        return g, ff
+
+    def run_control_loop(self, pose, iterations, use_feedback_gains=False):
+        """The reference's own runControlLoop (PI/run_control_loop.cuh:84-321) in debug mode -- two fresh controllers sharing
+        this model and cost object, the loop integrating the model as the plant -- for `iterations` iterations (20 ms each,
+        real time) from pose (x, y, heading).  Returns the per-iteration record, including the N(0,1) draws consumed."""
+        n, T, N = int(iterations), self.T, self.N
+        out = dict(states=np.zeros((n, 7), np.float32), controls=np.zeros((n, 2), np.float32), controller_used=np.zeros(n, np.int32),
+                   trajectory_costs=np.zeros((n, 2), np.float32), U_actual=np.zeros((n, T, 2), np.float32),
+                   U_predicted=np.zeros((n, T, 2), np.float32), gains=np.zeros((n, T, 2, 7), np.float32),
+                   eps=np.zeros((n, N, T, 2), np.float32))
+        rc = lib().ref_run_control_loop(self._h, _fp(_f32(pose, 3)), n, int(bool(use_feedback_gains)), _fp(out["states"]), _fp(out["controls"]),
+                                        out["controller_used"].ctypes.data_as(ctypes.POINTER(ctypes.c_int)), _fp(out["trajectory_costs"]),
+                                        _fp(out["U_actual"]), _fp(out["U_predicted"]), _fp(out["gains"]), _fp(out["eps"]))
+        if rc != 0:
+            raise RuntimeError("ref_run_control_loop failed: %d" % rc)
+        return out
+
     def time_kernels(self, state, reps=20):
         """Device time (ms) of the reference's four GPU stages per computeControl iteration, kernels alone:
         {curand, rollout, normexp, weighted_reduction} (oracle/ref_harness.cu::time_kernels)."""

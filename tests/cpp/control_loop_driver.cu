@@ -3,12 +3,15 @@
 // runControlLoop in debug mode (the host model is the plant) for `profiler_max_iter` iterations.  Writes the executed
 // state / control log for the closed-loop test (tests/test_control_loop.py).
 //
-// usage: control_loop_driver <nn|bf> <launch_file> <out.npz> <iterations> <x> <y> <heading> [double_step [swap.npz swap_iteration]]
+// usage: control_loop_driver <nn|bf> <launch_file> <out.npz> <iterations> <x> <y> <heading> [double_step [swap.npz swap_iteration
+//        [noise.bin use_feedback_gains]]]   (swap.npz may be "-"; noise.bin holds [iterations][NUM_ROLLOUTS][T][2] float32 draws that are
+//        injected into BOTH controllers, as the reference's two cuRAND generators, both seeded 1234, draw the same sequence)
 //   swap.npz: arrays `description` (int32 layer widths) and `data` (float32, all weights then all biases): the flattened
 //   /model_updater/model message, handed to the loop after `swap_iteration` iterations (model hot swap).
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
+#include <fstream>
 #include <map>
 #include <string>
 #include <vector>
@@ -35,7 +38,7 @@ int run(int argc, char **argv) {
   params["heading"] = XmlRpc::XmlRpcValue(atof(argv[7]));
   params["debug_mode"] = XmlRpc::XmlRpcValue(true);
   params["sleep_to_rate"] = XmlRpc::XmlRpcValue(false);
-  params["use_feedback_gains"] = XmlRpc::XmlRpcValue(false);
+  params["use_feedback_gains"] = XmlRpc::XmlRpcValue(argc > 12 && atoi(argv[12]) != 0);
   params["reference_debug_double_step"] = XmlRpc::XmlRpcValue(argc > 8 && atoi(argv[8]) != 0);
   MPPICosts *costs = new MPPICosts(&params);
   float2 control_constraints[2] = {make_float2(-.99, .99), make_float2(-.99, (double)params["max_throttle"])};
@@ -51,7 +54,15 @@ int run(int argc, char **argv) {
   Controller *actual = new Controller(model, costs, exploration_std, init_u, hz, T, stride, gamma, num_iters);
   Controller *predicted = new Controller(model, costs, exploration_std, init_u, hz, T, stride, gamma, num_iters);
   SimPlant robot((float)atof(argv[5]), (float)atof(argv[6]), (float)atof(argv[7]));
-  if (argc > 10) {
+  if (argc > 11) {
+    std::ifstream nf(argv[11], std::ios::binary | std::ios::ate);
+    const size_t bytes = (size_t)nf.tellg();
+    nf.seekg(0);
+    std::vector<float> noise(bytes / sizeof(float));
+    nf.read(reinterpret_cast<char *>(noise.data()), (std::streamsize)bytes);
+    robot.setInjectedNoise(std::move(noise), (size_t)Controller::NUM_ROLLOUTS * T * 2);
+  }
+  if (argc > 10 && std::string(argv[9]) != "-") {
     npz::Archive swap = npz::load(argv[9]);
     const npz::Array &d = swap.at("description"), &v = swap.at("data");
     std::vector<int> description(d.num_vals());
@@ -70,6 +81,12 @@ int run(int argc, char **argv) {
   w.add("controls", ct.data(), {n, 2});
   std::vector<float> used(robot.controllerUsed().begin(), robot.controllerUsed().end());
   w.add("controller_used", used.data(), {used.size()});
+  if (!robot.trajectoryCosts().empty()) {
+    w.add("trajectory_costs", robot.trajectoryCosts().data(), {used.size(), 2});
+    w.add("gains", robot.loggedGains().data(), {used.size(), (size_t)T, 2, 7});
+    w.add("U_actual", robot.loggedUActual().data(), {used.size(), (size_t)T, 2});
+    w.add("U_predicted", robot.loggedUPredicted().data(), {used.size(), (size_t)T, 2});
+  }
   const float tick = (float)robot.avgTickMs();
   w.add("avg_tick_ms", &tick, {1});
   w.save(argv[3]);

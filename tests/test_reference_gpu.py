@@ -291,3 +291,88 @@ def test_reference_kernel_times_are_reported(models, costmap):
     print("reference kernels (ms): %s; computeControl %.3f ms" % (k, e2e))
     assert all(v > 0 for v in k.values()) and sum(k.values()) < e2e
     np.testing.assert_array_equal(V[7, 1:], (straight_controls(100)[1:] + want["eps"][0, 7, 1:] * NU).astype(np.float32))
+
+
+# ---- SURVEY section 8 f-2 / f-1 pinned on the reference's own DDP and runControlLoop (oracle/ref_harness.cu) ----
+
+def _gain_errors(got, want):
+    """Per timestep ||K_k - K_k_ref||_F / ||K_k_ref||_F over the steps that carry a gain (the last one is zero by construction)."""
+    num = np.sqrt(((got - want) ** 2).sum(axis=(-1, -2)))
+    den = np.sqrt((want ** 2).sum(axis=(-1, -2)))
+    m = den > 1e-6 * den.max()
+    return (num[m] / den[m])
+
+
+@pytest.mark.parametrize("kind", ["nn", "bf"])
+def test_feedback_gains_match_reference_ddp(tmp_path, models, costmap, kind):
+    """computeFeedbackGains: the reference's DDP<ModelWrapperDDP<MODEL>>::run with TrackingCostDDP (DDP/ddp.h:49-157,
+    DDP/ddp_tracking_costs.h:7-117, analytic NeuralNetModel::computeGrad or Eigen::NumericalDiff for the basis functions), compiled
+    from its sources, against include/autorally_control/ddp/ddp_feedback.h through the drop-in MPPIController template.  Both
+    controllers plan from the same state on the same noise (the reference's cuRAND draws), then linearise around their own
+    solutions."""
+    import os
+    import subprocess
+    from autorally_b200.params import BF_DEFAULTS, NN_DEFAULTS
+    from tests.test_host_cpp import LIB, write_inputs
+    dflt = NN_DEFAULTS if kind == "nn" else BF_DEFAULTS
+    cp = cost_params_for(costmap, desired_speed=dflt.get("desired_speed", 8.0))
+    state = default_state(5.0)
+    T = 100
+    init_u = tuple(float(v) for v in dflt["init_u"])
+    U0 = np.broadcast_to(np.asarray(init_u, np.float32), (T, 2)).copy()
+    theta = models["autorally_nnet_theta"] if kind == "nn" else models["basis_function_W"]
+    with ref.ReferenceController(ref.REF_NN_1920 if kind == "nn" else ref.REF_BF_2560, theta, costmap, cp, init_u=init_u) as rc:
+        rc.set_controls(U0, np.zeros(4, np.float32))
+        want = rc.compute_control(state)
+        g_ref, ff_ref = rc.feedback_gains(state)
+    np.concatenate([want["eps"][0].ravel(), want["eps"][0].ravel()]).astype(np.float32).tofile(tmp_path / "noise.bin")
+    launch, env = write_inputs(tmp_path, models, costmap, kind)
+    subprocess.check_call([os.path.join(LIB, "host_api_driver"), kind, launch, str(tmp_path / "noise.bin"), str(tmp_path / "out.npz")] +
+                          [repr(float(v)) for v in state], env=env)
+    got = np.load(tmp_path / "out.npz")
+    assert rel_err(got["state_solution1"], want["state_solution"]).max() < 2e-4   # the trajectories the gains linearise around agree
+    err = _gain_errors(got["feedback_gain"], g_ref)
+    print("%s feedback gains vs the reference's DDP: max relative (Frobenius, per step) %.3g, median %.3g, |K| max %.3g" % (
+        kind, err.max(), np.median(err), np.abs(g_ref).max()))
+    assert np.abs(g_ref[:50]).max() > 1e-3 and np.all(g_ref[-1] == 0)
+    # NN: analytic Jacobians on both sides.  BF: both sides difference the model numerically with h = sqrt(eps) |x| in float32
+    # (DDP/ddp_dynamics.h:79-83), i.e. steps of ~1e-7 on the small state components; the two Jacobians are equally noisy
+    # and differ in their noise.
+    assert err.max() < (1e-3 if kind == "nn" else 0.5), err.max()
+
+
+def test_run_control_loop_tracks_the_reference_loop(tmp_path, models, costmap):
+    """The reference's own runControlLoop (PI/run_control_loop.cuh:84-321; debug mode, two controllers sharing model and costs,
+    arbitration on getComputedTrajectoryCost :250-285, feedback gains on) against the drop-in loop of
+    include/autorally_control/path_integral/run_control_loop.cuh, free-running for 50 iterations from the same pose on the same
+    noise.  The reference's two controllers both seed cuRAND with 1234, so they draw the SAME sequence; the drop-in loop is
+    given those draws for both of its controllers, and the reference's debug-plant double step."""
+    import os
+    import subprocess
+    from tests.test_host_cpp import LIB, write_inputs
+    cp = cost_params_for(costmap)
+    n, pose = 50, (0.0, 12.0, float(np.pi))
+    with ref.ReferenceController(ref.REF_NN_1920, models["autorally_nnet_theta"], costmap, cp) as rc:
+        want = rc.run_control_loop(pose, n, use_feedback_gains=True)
+    assert set(np.unique(want["controller_used"])) == {0, 1}, "the reference trace must exercise both branches of the arbitration"
+    want["eps"].tofile(tmp_path / "noise.bin")
+    launch, env = write_inputs(tmp_path, models, costmap, "nn")
+    out = tmp_path / "loop.npz"
+    subprocess.check_call([os.path.join(LIB, "control_loop_driver"), "nn", launch, str(out), str(n)] + [repr(float(v)) for v in pose] +
+                          ["1", "-", "0", str(tmp_path / "noise.bin"), "1"], env=env)
+    got = np.load(out)
+    used = got["controller_used"].astype(np.int32)
+    tc_w, tc_g = want["trajectory_costs"], got["trajectory_costs"]
+    gap = np.abs(tc_w[:, 0] - tc_w[:, 1]) / np.maximum(np.abs(tc_w).max(axis=1), 1e-30)
+    print("controller_used reference %s\n                drop-in   %s" % ("".join(map(str, want["controller_used"])), "".join(map(str, used))))
+    print("smallest relative gap between the two trajectory costs in the reference run (iterations with a gap): %.3g; max state diff %.3g; "
+          "max trajectory-cost rel diff %.3g" % (gap[gap > 0].min() if (gap > 0).any() else 0.0, np.abs(got["states"] - want["states"]).max(),
+                                               (np.abs(tc_g - tc_w) / np.abs(tc_w)).max()))
+    np.testing.assert_array_equal(used, want["controller_used"])
+    np.testing.assert_allclose(got["states"], want["states"], rtol=2e-3, atol=2e-3)
+    np.testing.assert_allclose(got["controls"], want["controls"], rtol=0, atol=2e-3)
+    np.testing.assert_allclose(tc_g, tc_w, rtol=5e-3)
+    # the gains handed to the plant every iteration (chosen controller's), per step of the horizon
+    worst = max(_gain_errors(got["gains"][i], want["gains"][i]).max() for i in range(n))
+    print("feedback gains handed over, worst relative (Frobenius, per step) over %d iterations: %.3g" % (n, worst))
+    assert worst < 2e-2, worst

@@ -23,7 +23,7 @@ def main():
     ap.add_argument("--tag", default="autorally_nnet", help="model in tests/golden/ref_models.npz (wider_deeper = 6-64-64-64-64-4)")
     a = ap.parse_args()
     from autorally_b200.params import ellipse_states, make_ellipse_costmap
-    from tests.common import cost_params_for, default_state, make_context, warm_controls
+    from autorally_b200.scenarios import cost_params_for, default_state, make_context, warm_controls
     models = np.load(os.path.join(ROOT, "tests", "golden", "ref_models.npz"))
     costmap = make_ellipse_costmap()
     cp = cost_params_for(costmap)
