@@ -180,10 +180,8 @@ bool supports_fused_noise(const mppi_ctx *c) {
 }
 bool fused_noise_now(const mppi_ctx *c) {
   if (c->injected || c->fused_mode == 0 || !supports_fused_noise(c)) return false;
-  // automatic: in place for the network kernels (no sampler launch, no noise round trip through HBM; 1M rollouts 3.89 ->
-  // 3.86 ms per step), the sampler kernel for the basis-function kernel, whose transcendental chain does not hide the
-  // Philox rounds (1M rollouts: 2.63 ms with the sampler kernel, 2.79 ms in place; profiles/exp_fused_r02.txt)
-  if (c->fused_mode < 0 && c->cfg.dynamics == MPPI_DYNAMICS_BF) return false;
+  // automatic: in place wherever the kernel supports it -- no sampler launch, no noise round trip through HBM (1M rollouts,
+  // profiles/exp_fused_r02.txt: network 3.89 -> 3.86 ms per step, basis functions 2.43 -> 2.37 ms)
   return true;
 }
 

@@ -368,11 +368,26 @@ def test_run_control_loop_tracks_the_reference_loop(tmp_path, models, costmap):
     print("smallest relative gap between the two trajectory costs in the reference run (iterations with a gap): %.3g; max state diff %.3g; "
           "max trajectory-cost rel diff %.3g" % (gap[gap > 0].min() if (gap > 0).any() else 0.0, np.abs(got["states"] - want["states"]).max(),
                                                (np.abs(tc_g - tc_w) / np.abs(tc_w)).max()))
-    np.testing.assert_array_equal(used, want["controller_used"])
-    np.testing.assert_allclose(got["states"], want["states"], rtol=2e-3, atol=2e-3)
-    np.testing.assert_allclose(got["controls"], want["controls"], rtol=0, atol=2e-3)
-    np.testing.assert_allclose(tc_g, tc_w, rtol=5e-3)
-    # the gains handed to the plant every iteration (chosen controller's), per step of the horizon
-    worst = max(_gain_errors(got["gains"][i], want["gains"][i]).max() for i in range(n))
-    print("feedback gains handed over, worst relative (Frobenius, per step) over %d iterations: %.3g" % (n, worst))
+    # A free-running closed loop can only be compared up to the first near-tie of the arbitration: where the two trajectory costs
+    # are within 5e-4 of each other the parity of one computeControl no longer fixes the sign of their difference, the two
+    # loops may pick different controllers and are different experiments from there on.
+    close = np.nonzero(gap < 5e-4)[0]
+    m = int(close[0]) if len(close) else n
+    print("comparing the first %d iterations (first near-tie of the reference's two trajectory costs at iteration %d, gap %.3g)" % (
+        m, m, gap[m] if m < n else float("nan")))
+    assert m >= 12 and set(np.unique(want["controller_used"][:m])) == {0, 1}
+    # the arbitration rule itself (:250-251: the measured-state plan wins only with the strictly smaller cost), all 50 iterations, both loops
+    np.testing.assert_array_equal(want["controller_used"], np.where(tc_w[:, 0] < tc_w[:, 1], 0, 1))
+    np.testing.assert_array_equal(used, np.where(tc_g[:, 0] < tc_g[:, 1], 0, 1))
+    np.testing.assert_array_equal(used[:m], want["controller_used"][:m])
+    np.testing.assert_allclose(got["states"][:m], want["states"][:m], rtol=1e-3, atol=1e-3)
+    np.testing.assert_allclose(got["controls"][:m], want["controls"][:m], rtol=0, atol=1e-3)
+    np.testing.assert_allclose(tc_g[:m], tc_w[:m], rtol=2e-3)
+    # the sequences each controller holds after the iteration (the predicted-state controller adopts the winner's when the
+    # measured-state plan wins, PI/run_control_loop.cuh:259-260)
+    np.testing.assert_allclose(got["U_actual"][:m], want["U_actual"][:m], rtol=0, atol=2e-3)
+    np.testing.assert_allclose(got["U_predicted"][:m], want["U_predicted"][:m], rtol=0, atol=2e-3)
+    # the gains handed to the plant every iteration (the chosen controller's), per step of the horizon
+    worst = max(_gain_errors(got["gains"][i], want["gains"][i]).max() for i in range(m))
+    print("feedback gains handed over, worst relative (Frobenius, per step) over the first %d iterations: %.3g" % (m, worst))
     assert worst < 2e-2, worst
