@@ -102,6 +102,11 @@ struct mppi_ctx {
   int launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::vector<cudaEvent_t> step_events;
+  // device-resident stepping: the nominal trajectory of step k (finalize phase 2) runs on side_stream beside the rollouts
+  // of step k + 1; ev_fin orders it after phase 1 of its own step, ev_nom orders phase 1 of the next step after it
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_fin = nullptr, ev_nom = nullptr;
+  bool split_finalize = false, nominal_pending = false;
   void *d_flush = nullptr;
 };
 
@@ -161,9 +166,9 @@ int resolve_variant(const mppi_ctx *c) {
 }
 
 template <class K, class P>
-cudaError_t launch_pdl(mppi_ctx *c, K kernel, dim3 grid, int block, size_t smem, bool pdl, const P &params) {
+cudaError_t launch_pdl(mppi_ctx *c, K kernel, dim3 grid, int block, size_t smem, bool pdl, const P &params, cudaStream_t stream = nullptr) {
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid; cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
+  cfg.gridDim = grid; cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = stream ? stream : c->stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -199,14 +204,19 @@ cudaError_t launch_rollout(mppi_ctx *c) {
   p.seed_lo = (uint32_t)c->seed; p.seed_hi = (uint32_t)(c->seed >> 32); p.call_ptr = c->d_call_counter;
   const long long total = (long long)c->B * c->n_local;
   const bool small = total <= 148LL * 4 * 32 * 4;
+  // The tensor-core kernel overlaps its prologue with its predecessor only when that predecessor is the SHORT finalize
+  // phase 1 of split stepping: its tiles, waiting in griddepcontrol.wait on every SM, slow a co-resident single-warp
+  // nominal trajectory down (131072 rollouts, resident stepping: 0.632 ms without the attribute, 0.679 ms with it next to
+  // the unsplit finalize kernel, 0.606 ms with it next to phase 1; profiles/exp_overlap_r02.txt)
+  const bool tc_pdl = c->pdl && !c->injected && c->split_finalize;
   c->launches++;
   if (c->cfg.dynamics == MPPI_DYNAMICS_BF) return launch_rollout_bf(p, c->stream, small);
   if (c->variant == MPPI_ROLLOUT_GENERIC) return launch_rollout_generic(p, c->stream, c->net_structure.data(), (int)c->net_structure.size());
   if (c->net_kind == 64)
-    return c->variant == MPPI_ROLLOUT_TENSOR ? launch_rollout_nn64_tc(p, c->stream, c->theta_t.data()) : launch_rollout_nn64_r1(p, c->stream, small);
+    return c->variant == MPPI_ROLLOUT_TENSOR ? launch_rollout_nn64_tc(p, c->stream, c->theta_t.data(), tc_pdl) : launch_rollout_nn64_r1(p, c->stream, small);
   switch (c->variant) {
     case MPPI_ROLLOUT_THREAD2: return launch_rollout_nn32_r2(p, c->stream, small);
-    case MPPI_ROLLOUT_TENSOR: return launch_rollout_nn32_tc(p, c->stream, c->theta_t.data());
+    case MPPI_ROLLOUT_TENSOR: return launch_rollout_nn32_tc(p, c->stream, c->theta_t.data(), tc_pdl);
     case MPPI_ROLLOUT_HALF16: return launch_rollout_nn32_half(p, c->stream, c->pdl && !c->injected);
     default: return launch_rollout_nn32_r1(p, c->stream, small);
   }
@@ -245,7 +255,7 @@ size_t finalize_smem(const mppi_ctx *c) {
   return (4 * (size_t)c->T + 2 * FIN_MAX_WIDTH + nparams) * sizeof(float);
 }
 
-cudaError_t launch_finalize(mppi_ctx *c, const float *gathered, int G, int last_iter, int feed_back, bool push_outbox = false) {
+cudaError_t launch_finalize_phase(mppi_ctx *c, const float *gathered, int G, int last_iter, int feed_back, bool push_outbox, int phase) {
   FinalizeParams p{};
   if (c->direct_combine && gathered == c->d_shard) { gathered = c->d_block_partials; p.combine_partials = c->nblk; }
   p.gathered = gathered; p.inbox = c->d_inbox; p.outbox = push_outbox ? c->h_outbox_dev : c->d_outbox; p.theta_t = c->d_theta_t;
@@ -260,15 +270,49 @@ cudaError_t launch_finalize(mppi_ctx *c, const float *gathered, int G, int last_
   p.baseline = c->d_baseline; p.call_counter = c->d_call_counter;
   p.p2p_flags = (c->p2p_send && gathered == c->p2p_mailbox_half()) ? c->p2p_flags : nullptr;
   p.p2p_seq = c->p2p_seq; p.p2p_error = c->d_p2p_error;
+  p.phase = phase;
   c->launches++;
   // after an NCCL exchange (gathered != own shard) the predecessor is not one of our kernels: plain launch
   // many batched controllers: small CTAs, so that more of the single-warp nominal trajectories are resident per SM
-  const bool pdl = c->pdl && (gathered == c->d_shard || p.combine_partials > 0);
+  const bool pdl = phase != 2 && c->pdl && (gathered == c->d_shard || p.combine_partials > 0);
+  cudaStream_t st = phase == 2 ? c->side_stream : c->stream;
   const int threads = c->B >= 64 ? 64 : 256;
-  if (p.is_nn32) return launch_pdl(c, finalize_kernel<32>, dim3(c->B), threads, finalize_smem(c), pdl, p);
-  if (p.is_nn64 && threads == 256) return launch_pdl(c, finalize_kernel<64>, dim3(c->B), threads, finalize_smem(c), pdl, p);
-  return launch_pdl(c, finalize_kernel<0>, dim3(c->B), threads, finalize_smem(c), pdl, p);
+  // the nominal trajectory of the 6-32-32-4 network lives on ONE warp: launched alone (phase 2) it takes 4K registers and
+  // finds room on an SM whose register file the next step's rollout tiles have already claimed
+  if (p.is_nn32) return launch_pdl(c, finalize_kernel<32>, dim3(c->B), phase == 2 ? 32 : threads, finalize_smem(c), pdl, p, st);
+  if (p.is_nn64 && threads == 256) return launch_pdl(c, finalize_kernel<64>, dim3(c->B), threads, finalize_smem(c), pdl, p, st);
+  return launch_pdl(c, finalize_kernel<0>, dim3(c->B), threads, finalize_smem(c), pdl, p, st);
 }
+
+// One finalize launch, or -- in device-resident stepping (split_finalize) -- its two phases: control update + smoothing on the
+// context's stream, the nominal trajectory on the side stream so that it runs beside the next step's rollouts.
+cudaError_t launch_finalize(mppi_ctx *c, const float *gathered, int G, int last_iter, int feed_back, bool push_outbox = false) {
+  if (!c->split_finalize || !last_iter) return launch_finalize_phase(c, gathered, G, last_iter, feed_back, push_outbox, 0);
+  cudaError_t e;
+  // phase 1 of this step rewrites the outbox the previous step's nominal trajectory reads its controls from
+  if (c->nominal_pending && (e = cudaStreamWaitEvent(c->stream, c->ev_nom, 0)) != cudaSuccess) return e;
+  if ((e = launch_finalize_phase(c, gathered, G, last_iter, feed_back, push_outbox, 1)) != cudaSuccess) return e;
+  if ((e = cudaEventRecord(c->ev_fin, c->stream)) != cudaSuccess) return e;
+  if ((e = cudaStreamWaitEvent(c->side_stream, c->ev_fin, 0)) != cudaSuccess) return e;
+  if ((e = launch_finalize_phase(c, gathered, G, last_iter, feed_back, push_outbox, 2)) != cudaSuccess) return e;
+  if ((e = cudaEventRecord(c->ev_nom, c->side_stream)) != cudaSuccess) return e;
+  c->nominal_pending = true;
+  return cudaSuccess;
+}
+
+// Scope guard of the split: joins the side stream back into the context's stream on exit, so that whatever follows (the
+// end-of-batch event, a host copy) sees the last nominal trajectory.
+struct SplitFinalizeScope {
+  mppi_ctx *c;
+  explicit SplitFinalizeScope(mppi_ctx *ctx, bool on) : c(ctx) { c->split_finalize = on && c->side_stream != nullptr && std::getenv("MPPI_NO_SPLIT_FINALIZE") == nullptr; }
+  cudaError_t join() {
+    cudaError_t e = cudaSuccess;
+    if (c->nominal_pending) e = cudaStreamWaitEvent(c->stream, c->ev_nom, 0);
+    c->nominal_pending = false;
+    return e;
+  }
+  ~SplitFinalizeScope() { join(); c->split_finalize = false; }
+};
 
 int check_ready(const mppi_ctx *c) {
   if (!c) return MPPI_ERR_INVALID_ARG;
@@ -386,6 +430,9 @@ int mppi_create(const mppi_config *cfg, mppi_ctx **out) {
   CKF(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CKF(cudaEventCreate(&c->ev0));
   CKF(cudaEventCreate(&c->ev1));
+  CKF(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+  CKF(cudaEventCreateWithFlags(&c->ev_fin, cudaEventDisableTiming));
+  CKF(cudaEventCreateWithFlags(&c->ev_nom, cudaEventDisableTiming));
   const size_t B = c->B, n = c->n_local, T = c->T;
   CKF(cudaMalloc(&c->d_inbox, B * c->inbox_stride * sizeof(float)));
   CKF(cudaMalloc(&c->d_outbox, B * c->outbox_stride * sizeof(float)));
@@ -437,6 +484,9 @@ int mppi_destroy(mppi_ctx *c) {
   for (cudaEvent_t e : c->step_events) cudaEventDestroy(e);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->side_stream) { cudaStreamSynchronize(c->side_stream); cudaStreamDestroy(c->side_stream); }
+  if (c->ev_fin) cudaEventDestroy(c->ev_fin);
+  if (c->ev_nom) cudaEventDestroy(c->ev_nom);
   if (c->stream && c->owns_stream) cudaStreamDestroy(c->stream);
   cudaGetLastError();
   delete c;
@@ -1009,11 +1059,13 @@ int mppi_run_resident_sharded(mppi_ctx *c, int steps, float *elapsed_ms) {
   if (steps < 1 || !c->have_inbox || c->injected || (!c->nccl_comm && c->p2p_size <= 1)) return MPPI_ERR_INVALID_ARG;
   CK(cudaSetDevice(c->device));
   c->launches = 0;
+  SplitFinalizeScope split(c, true);
   CK(cudaEventRecord(c->ev0, c->stream));
   for (int s = 0; s < steps; s++) {
     rc = enqueue_sharded(c, 1);
     if (rc) return rc;
   }
+  CK(split.join());  // the timed region ends after the last nominal trajectory
   CK(cudaEventRecord(c->ev1, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   float ms = 0.0f;
@@ -1038,6 +1090,9 @@ int mppi_run_resident(mppi_ctx *c, int steps, int flush_l2, float *elapsed_ms, f
   if (flush_l2 && !c->d_flush) CK(cudaMalloc(&c->d_flush, kFlushBytes));
   c->launches = 0;
   DirectCombineScope direct(c);
+  // back-to-back steps: the nominal trajectory of a step overlaps the next step's rollouts.  Not with per-step intervals
+  // (L2 flush / kernel timing): there every step is timed on its own and must contain all of its work.
+  SplitFinalizeScope split(c, !per_step);
   CK(cudaEventRecord(c->ev0, c->stream));
   for (int s = 0; s < steps; s++) {
     if (flush_l2) CK(cudaMemsetAsync(c->d_flush, s & 0xff, kFlushBytes, c->stream));
@@ -1053,6 +1108,7 @@ int mppi_run_resident(mppi_ctx *c, int steps, int flush_l2, float *elapsed_ms, f
     }
     if (per_step) CK(cudaEventRecord(c->step_events[4 * s + 1], c->stream));
   }
+  CK(split.join());  // the timed region ends after the last nominal trajectory
   CK(cudaEventRecord(c->ev1, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   float total = 0.0f, roll = 0.0f;

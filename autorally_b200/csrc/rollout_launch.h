@@ -11,8 +11,8 @@ cudaError_t launch_rollout_nn32_r2(const RolloutParams &p, cudaStream_t st, bool
 // pdl: launch with programmatic stream serialization (the kernel overlaps its prologue with its predecessor's tail)
 cudaError_t launch_rollout_nn32_half(const RolloutParams &p, cudaStream_t st, bool pdl);
 // tcgen05 tensor-core MLP (FP16 hi/lo split, activations in tensor memory): the filled-GPU kernel
-cudaError_t launch_rollout_nn32_tc(const RolloutParams &p, cudaStream_t st, const float *host_theta_t);
-cudaError_t launch_rollout_nn64_tc(const RolloutParams &p, cudaStream_t st, const float *host_theta_t);  // 6-64-64-64-64-4
+cudaError_t launch_rollout_nn32_tc(const RolloutParams &p, cudaStream_t st, const float *host_theta_t, bool pdl);
+cudaError_t launch_rollout_nn64_tc(const RolloutParams &p, cudaStream_t st, const float *host_theta_t, bool pdl);  // 6-64-64-64-64-4
 bool tc_biases_in_range(const float *host_theta_t, int hid, int nhid);
 cudaError_t launch_rollout_nn64_r1(const RolloutParams &p, cudaStream_t st, bool small);
 cudaError_t launch_rollout_bf(const RolloutParams &p, cudaStream_t st, bool small);

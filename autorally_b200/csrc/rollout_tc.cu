@@ -305,6 +305,11 @@ rollout_tc_kernel(const __grid_constant__ RolloutParams p, const __grid_constant
 
   const uint32_t sb = (smem_u32(smem) & 0x3FFFFu) >> 4;
   constexpr uint32_t IDH = idesc(128, HID), ID16 = idesc(128, 16);
+  // Programmatic dependent launch: everything above (weights -> FP16 B matrices, tensor-memory allocation) reads model
+  // parameters only and overlaps the tail of the previous kernel of the stream (the finalize kernel of the previous step);
+  // the inbox, the call counter and the noise buffer are read after the wait.
+  pdl_trigger();
+  pdl_wait();
 
   // ---- rollout bookkeeping (rollout.cuh, R = 1) ----
   const long long total = (long long)p.B * p.n_local;
@@ -489,7 +494,7 @@ rollout_tc_kernel(const __grid_constant__ RolloutParams p, const __grid_constant
 }  // namespace tc
 
 template <int HID, int NHID, int TPC, bool FUSED>
-static cudaError_t launch_tc_f(const RolloutParams &p, cudaStream_t st, const float *host_theta_t) {
+static cudaError_t launch_tc_f(const RolloutParams &p, cudaStream_t st, const float *host_theta_t, bool pdl) {
   using G = tc::Geo<HID, NHID, TPC>;
   const long long total = (long long)p.B * p.n_local;
   const unsigned grid = (unsigned)((total + G::THREADS - 1) / G::THREADS);
@@ -528,20 +533,25 @@ static cudaError_t launch_tc_f(const RolloutParams &p, cudaStream_t st, const fl
     }
     smem_bytes = bytes;
   }
-  tc::rollout_tc_kernel<HID, NHID, TPC, FUSED><<<grid, G::THREADS, smem_bytes, st>>>(p, ep);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(G::THREADS); cfg.dynamicSmemBytes = (size_t)smem_bytes; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, tc::rollout_tc_kernel<HID, NHID, TPC, FUSED>, p, ep);
 }
 
 template <int HID, int NHID, int TPC>
-static cudaError_t launch_tc(const RolloutParams &p, cudaStream_t st, const float *host_theta_t) {
-  return p.fused_noise ? launch_tc_f<HID, NHID, TPC, true>(p, st, host_theta_t) : launch_tc_f<HID, NHID, TPC, false>(p, st, host_theta_t);
+static cudaError_t launch_tc(const RolloutParams &p, cudaStream_t st, const float *host_theta_t, bool pdl) {
+  return p.fused_noise ? launch_tc_f<HID, NHID, TPC, true>(p, st, host_theta_t, pdl) : launch_tc_f<HID, NHID, TPC, false>(p, st, host_theta_t, pdl);
 }
 
-cudaError_t launch_rollout_nn32_tc(const RolloutParams &p, cudaStream_t st, const float *host_theta_t) { return launch_tc<32, 2, 1>(p, st, host_theta_t); }
-cudaError_t launch_rollout_nn64_tc(const RolloutParams &p, cudaStream_t st, const float *host_theta_t) {
+cudaError_t launch_rollout_nn32_tc(const RolloutParams &p, cudaStream_t st, const float *host_theta_t, bool pdl) { return launch_tc<32, 2, 1>(p, st, host_theta_t, pdl); }
+cudaError_t launch_rollout_nn64_tc(const RolloutParams &p, cudaStream_t st, const float *host_theta_t, bool pdl) {
   // up to two one-tile CTAs per SM: spread the tiles; beyond that, two tiles per CTA share the weights (4 tiles per SM)
   const long long tiles = ((long long)p.B * p.n_local + tc::TILE - 1) / tc::TILE;
-  return tiles <= 2 * 148 ? launch_tc<64, 4, 1>(p, st, host_theta_t) : launch_tc<64, 4, 2>(p, st, host_theta_t);
+  return tiles <= 2 * 148 ? launch_tc<64, 4, 1>(p, st, host_theta_t, pdl) : launch_tc<64, 4, 2>(p, st, host_theta_t, pdl);
 }
 
 // True when every folded bias of the network keeps e^(2 b) inside the FP32 range (|b| < 40); otherwise the caller uses

@@ -276,6 +276,10 @@ struct FinalizeParams {
   const unsigned int *p2p_flags;  // this GPU's flags [2][G][B]; nullptr = no peer exchange
   unsigned int p2p_seq;
   unsigned int *p2p_error;
+  // 0: the whole kernel.  Device-resident stepping splits it so that the nominal trajectory -- a 100-step dependent chain on
+  // one warp that only produces outputs -- runs on a second stream beside the NEXT step's rollouts:
+  // 1: combine + control update + smoothing (+ feed-back) only; 2: nominal trajectory only (reads the smoothed U from the outbox).
+  int phase;
 };
 
 constexpr int FIN_MAX_WIDTH = 128;
@@ -525,10 +529,15 @@ __global__ void __launch_bounds__(256, NET == 0 ? 1 : 2) finalize_kernel(const _
   float *outbox = p.outbox + (size_t)b * p.outbox_stride;
   // warp 0 fetches its slices of the network while the other warps combine the shard records
   WarpMlp32 net;
-  if (NET == 32 && p.last_iter && tid < 32) net.load(p.theta_t, tid);
+  if (NET == 32 && p.last_iter && p.phase != 1 && tid < 32) net.load(p.theta_t, tid);
   CtaMlp<64, 4> net64;
-  if (NET == 64 && p.last_iter) net64.load(p.theta_t, tid & 63, tid >> 6);
+  if (NET == 64 && p.last_iter && p.phase != 1) net64.load(p.theta_t, tid & 63, tid >> 6);
+  pdl_trigger();  // the next step's first kernel may run its prologue (weights -> shared memory, tensor-memory allocation) now
   pdl_wait();  // the shard records come from the weighting kernel (or the exchange)
+  if (p.phase == 2) {  // nominal trajectory only: the smoothed controls were left in the outbox by the phase-1 launch
+    for (int k = tid; k < 2 * T; k += nthr) Usm[k] = outbox[4 + k];
+  }
+  if (p.phase != 2) {
   if (p.p2p_flags != nullptr) {
     if (tid < p.G) {
       const unsigned int *flag = p.p2p_flags + ((size_t)(p.p2p_seq & 1u) * p.G + tid) * p.B + b;
@@ -604,6 +613,13 @@ __global__ void __launch_bounds__(256, NET == 0 ? 1 : 2) finalize_kernel(const _
     Usm[k] = acc;
     outbox[4 + k] = acc;
   }
+  }  // phase != 2
+  if (p.phase == 1) {
+    __syncthreads();
+    if (p.feed_back)
+      for (int k = tid; k < 2 * T; k += nthr) inbox[INBOX_U + k] = Usm[k];
+    return;
+  }
   // stage the model parameters for the generic nominal trajectory (the 6-32-32-4 path holds them in registers)
   if (NET == 0) {
     int nparams = 100;
@@ -614,7 +630,7 @@ __global__ void __launch_bounds__(256, NET == 0 ? 1 : 2) finalize_kernel(const _
     for (int k = tid; k < nparams; k += nthr) sw[k] = p.theta_t[k];
   }
   __syncthreads();
-  if (p.feed_back)
+  if (p.feed_back && p.phase == 0)
     for (int k = tid; k < 2 * T; k += nthr) inbox[INBOX_U + k] = Usm[k];
   if (NET == 64) {
     __shared__ __align__(16) float act64[2 * 64];
