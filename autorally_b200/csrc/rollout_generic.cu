@@ -38,17 +38,25 @@ struct GenericNet {
 __device__ __forceinline__ void generic_layer(const float *__restrict__ W, const float *__restrict__ b, int nin, int nout, bool act,
                                               const float *__restrict__ cur, float *__restrict__ nxt, int lane) {
   if (nout <= 32) {
+    // one neuron per lane: k runs in four interleaved partial sums (k mod 4), as in the half-warp kernel and WarpMlp32 -- the
+    // dependent FMA chain is nin / 4 long instead of nin, and eight weight loads are in flight ahead of it
     if (lane < nout) {
       const float *w = W + lane;
-      float t = 0.0f;
-#pragma unroll 4
-      for (int k = 0; k < nin; k++) t = fmaf(w[(size_t)k * nout], cur[k], t);
-      t = __fadd_rn(t, b[lane]);
+      float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+      int k = 0;
+#pragma unroll 2
+      for (; k + 3 < nin; k += 4) {
+        const float w0 = w[(k + 0) * nout], w1 = w[(k + 1) * nout], w2 = w[(k + 2) * nout], w3 = w[(k + 3) * nout];
+        a0 = fmaf(w0, cur[k + 0], a0); a1 = fmaf(w1, cur[k + 1], a1); a2 = fmaf(w2, cur[k + 2], a2); a3 = fmaf(w3, cur[k + 3], a3);
+      }
+      for (; k < nin; k++) a0 = fmaf(w[k * nout], cur[k], a0);
+      const float t = __fadd_rn(__fadd_rn(__fadd_rn(a0, a1), __fadd_rn(a2, a3)), b[lane]);
       nxt[lane] = act ? tanh_fast(t) : t;
     }
     return;
   }
-  // up to four neurons per lane, four independent FMA chains; lanes past the end shadow neuron `lane` and store nothing
+  // up to four neurons per lane, four independent FMA chains (k ascending, bias last: the reference's order per neuron);
+  // lanes past the end shadow neuron `lane` and store nothing
   const int j0 = lane, j1 = lane + 32, j2 = lane + 64, j3 = lane + 96;
   const bool v1 = j1 < nout, v2 = j2 < nout, v3 = j3 < nout;
   const float *w0 = W + j0, *w1 = W + (v1 ? j1 : j0), *w2 = W + (v2 ? j2 : j0), *w3 = W + (v3 ? j3 : j0);
@@ -56,7 +64,7 @@ __device__ __forceinline__ void generic_layer(const float *__restrict__ W, const
 #pragma unroll 4
   for (int k = 0; k < nin; k++) {
     const float a = cur[k];
-    const size_t o = (size_t)k * nout;
+    const int o = k * nout;
     t0 = fmaf(w0[o], a, t0); t1 = fmaf(w1[o], a, t1); t2 = fmaf(w2[o], a, t2); t3 = fmaf(w3[o], a, t3);
   }
   t0 = __fadd_rn(t0, b[j0]);
@@ -66,17 +74,17 @@ __device__ __forceinline__ void generic_layer(const float *__restrict__ W, const
   if (v3) { t3 = __fadd_rn(t3, b[j3]); nxt[j3] = act ? tanh_fast(t3) : t3; }
 }
 
-__global__ void __launch_bounds__(512) rollout_generic_kernel(const __grid_constant__ RolloutParams p, const __grid_constant__ GenericNet net) {
+// SMEM_W: the weights are staged in shared memory (the compiler then emits LDS for them instead of generic loads)
+template <bool SMEM_W>
+__global__ void __launch_bounds__(512, 1) rollout_generic_kernel(const __grid_constant__ RolloutParams p, const __grid_constant__ GenericNet net) {
   extern __shared__ float4 gsm4[];
   float *sm = reinterpret_cast<float *>(gsm4);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const int T = p.T;
-  const int wfloats = net.weights_in_smem ? ((net.nparams + 3) & ~3) : 0;
-  const float *W = p.theta_t;
-  if (net.weights_in_smem) {
+  const int wfloats = SMEM_W ? ((net.nparams + 3) & ~3) : 0;
+  if (SMEM_W)
     for (int i = tid; i < wfloats / 4; i += blockDim.x) gsm4[i] = reinterpret_cast<const float4 *>(p.theta_t)[i];
-    W = sm;
-  }
+  const float *W = SMEM_W ? sm : p.theta_t;
   __syncthreads();
   float *act = sm + wfloats + (size_t)warp * (2 * GEN_ACT + ((T + 3) & ~3));
   float *scost = act + 2 * GEN_ACT;  // [T] step costs for the deferred running mean
@@ -217,12 +225,14 @@ cudaError_t launch_rollout_generic(const RolloutParams &p, cudaStream_t st, cons
     nwarps >>= 1;
   }
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  const unsigned grid = (unsigned)((total + nwarps - 1) / nwarps);
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(rollout_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = net.weights_in_smem ? cudaFuncSetAttribute(rollout_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                        : cudaFuncSetAttribute(rollout_generic_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  const unsigned grid = (unsigned)((total + nwarps - 1) / nwarps);
-  rollout_generic_kernel<<<grid, nwarps * 32, smem, st>>>(p, net);
+  if (net.weights_in_smem) rollout_generic_kernel<true><<<grid, nwarps * 32, smem, st>>>(p, net);
+  else rollout_generic_kernel<false><<<grid, nwarps * 32, smem, st>>>(p, net);
   return cudaGetLastError();
 }
 

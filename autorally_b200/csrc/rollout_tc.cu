@@ -307,8 +307,9 @@ rollout_tc_kernel(const __grid_constant__ RolloutParams p, const __grid_constant
   constexpr uint32_t IDH = idesc(128, HID), ID16 = idesc(128, 16);
   // Programmatic dependent launch: everything above (weights -> FP16 B matrices, tensor-memory allocation) reads model
   // parameters only and overlaps the tail of the previous kernel of the stream (the finalize kernel of the previous step);
-  // the inbox, the call counter and the noise buffer are read after the wait.
-  pdl_trigger();
+  // the inbox, the call counter and the noise buffer are read after the wait.  No early launch_dependents here: the weighting
+  // kernel's CTAs would become resident at once (a one-wave rollout grid leaves them room), and 4 x 256 threads per SM polling
+  // in griddepcontrol.wait for the whole rollout kernel cost it 11 % (131072 rollouts: 0.543 -> 0.606 ms).
   pdl_wait();
 
   // ---- rollout bookkeeping (rollout.cuh, R = 1) ----
