@@ -185,9 +185,13 @@ __global__ void __launch_bounds__(512, 1) rollout_generic_kernel(const __grid_co
     if (mine) scost[im] = cost;
   }
   __syncwarp();
-  // ---- running mean of the step costs, in step order (PI/mppi_controller.cu:162-165) ----
-  float running = 0.0f;
-  for (int i = 1; i < T; i++) running = (float)((double)running + (double)__fsub_rn(scost[i], running) * __ldg(p.inv_step + i));
+  // ---- running mean of the step costs (PI/mppi_controller.cu:162-165) = their arithmetic mean: summed in double over the
+  //      32 lanes in a fixed order and rounded once (see rollout_half.cu) ----
+  double csum = 0.0;
+  for (int i = 1 + lane; i < T; i += 32) csum += (double)scost[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) csum += __shfl_xor_sync(full, csum, o);
+  const float running = T > 1 ? (float)(csum * __ldg(p.inv_step + (T - 1))) : 0.0f;
   if (lane == 0) {
     p.costs[gro] = running;  // + terminalCost == 0 (PI/costs.cu:411-414)
     p.crash[gro] = (unsigned char)(crash_in ? 1 : 0);

@@ -14,9 +14,10 @@
 //    write-back, clamp; PI/mppi_controller.cu:130-159) and evaluates its running cost afterwards in parallel
 //    (positions by a sequential FMA prefix, sincosf, costmap fetches, PI/costs.cu:307-393; sticky crash flag as a
 //    prefix-OR over ballots);
-//  * the step costs go to shared memory and the running mean (float difference, double update,
-//    PI/mppi_controller.cu:162-165) is replayed once, in order, at the end: its double-precision dependent chain
-//    stalled the in-order pipeline when interleaved with the recursion (14% of the stall samples).
+//  * the step costs go to shared memory and their mean (the reference's running-mean recursion,
+//    PI/mppi_controller.cu:162-165) is taken once at the end, in double, by the 16 lanes in parallel: the recursion's
+//    float -> double -> float chain stalled the in-order pipeline when interleaved with the MLP (14% of the stall samples)
+//    and cost 2.8 us when replayed serially at the end.
 //
 // Layers 2 and 3 sum k in four interleaved partial sums (see warp_mlp.cuh for the numerical note).
 #include "rollout.cuh"
@@ -164,9 +165,17 @@ __global__ void __launch_bounds__(32, MINB) rollout_half_kernel(const __grid_con
     if (mine) scost[im] = cost;
   }
   __syncwarp();
-  // ---- running mean of the step costs, in step order (PI/mppi_controller.cu:162-165) ----
-  float running = 0.0f;
-  for (int i = 1; i < T; i++) running = (float)((double)running + (double)__fsub_rn(scost[i], running) * __ldg(p.inv_step + i));
+  // ---- running mean of the step costs (PI/mppi_controller.cu:162-165) ----
+  // The reference's recursion running += (c_i - running) / i is the arithmetic mean of c_1 .. c_{T-1}, rounded to float at
+  // every step.  Replaying it in order was a serial chain of T - 1 float -> double -> float updates (56 cycles each: 2.8 us
+  // of this kernel's 47 at T = 100); here the half-warp sums the costs in DOUBLE (fixed order: lane l takes steps 1 + l,
+  // 17 + l, ..., then an xor tree) and rounds once: a few float ulps (~1e-7 relative) from the recursion's value, inside
+  // the 1e-4 cost tolerance like every other difference between this kernel and the reference's arithmetic.
+  double csum = 0.0;
+  for (int i = 1 + l; i < T; i += 16) csum += (double)scost[i];
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) csum += __shfl_xor_sync(full, csum, o);
+  const float running = T > 1 ? (float)(csum * __ldg(p.inv_step + (T - 1))) : 0.0f;
   if (l == 0) {
     p.costs[gro] = running;  // + terminalCost == 0 (PI/costs.cu:411-414)
     p.crash[gro] = (unsigned char)(crash_in ? 1 : 0);

@@ -34,9 +34,11 @@ def compare(got, want, T, what, cost_tol=1e-4, u_tol=1e-4):
     np.testing.assert_array_equal(got["V"], want["V"], err_msg=what + ": sampled-control bookkeeping")
     check_costs(got["costs"], want["costs"], T, cost_tol)
     assert abs(got["costs"].min() - want["costs"].min()) <= cost_tol * (1 + abs(want["costs"].min())), what
-    for k in ("normalizer", "trajectory_cost"):   # truly relative (PI/mppi_controller.cu:641-652)
+    # truly relative (PI/mppi_controller.cu:641-652); widened by 4 gamma ulp(baseline): see tests/test_parity_gpu.py:check_scalars
+    wide = cost_tol + 4.0 * 0.5 * float(np.spacing(np.float32(abs(want["costs"].min()))))
+    for k in ("normalizer", "trajectory_cost"):
         g, w = float(got[k]), float(want[k])
-        assert abs(g - w) <= cost_tol * abs(w), "%s: %s got %.9g want %.9g" % (what, k, g, w)
+        assert abs(g - w) <= wide * abs(w), "%s: %s got %.9g want %.9g (bound %.3g)" % (what, k, g, w, wide)
     e = rel_err(got["U"], want["U"]).max()
     assert e < u_tol, "%s: max control rel err %.3g" % (what, e)
     tr = true_rel_err(got["U"], want["U"])   # reported; see tests/test_parity_gpu.py:TRUE_REL_BOUND for why it is not held to 1e-4
