@@ -38,6 +38,7 @@ EXPORTED_SYMBOLS = [
     "mppi_comm_unique_id", "mppi_comm_init", "mppi_comm_destroy", "mppi_compute_control_sharded",
     "mppi_run_resident_sharded", "mppi_compute_control_async", "mppi_compute_control_wait",
     "mppi_bench_compute_control", "mppi_p2p_export", "mppi_p2p_init", "mppi_p2p_destroy", "mppi_set_fused_noise",
+    "mppi_time_stages",
 ]
 
 
@@ -359,6 +360,12 @@ class MppiContext:
         self._ck(self.lib.mppi_run_resident(self._ctx, int(steps), int(bool(flush_l2)), ctypes.byref(el),
                                             ctypes.byref(rk) if time_rollout else None), "mppi_run_resident")
         return el.value, (rk.value if time_rollout else None)
+
+    def time_stages(self, reps=5):
+        """Device ms of {sampler kernel, rollout kernel, weighting kernel, finalize kernel}, each timed on its own."""
+        ms = (ctypes.c_float * 4)()
+        self._ck(self.lib.mppi_time_stages(self._ctx, int(reps), ms), "mppi_time_stages")
+        return dict(sampler=ms[0], rollout=ms[1], weighting=ms[2], finalize=ms[3])
 
     def last_launch_count(self):
         return self.lib.mppi_last_launch_count(self._ctx)

@@ -81,7 +81,8 @@ struct mppi_ctx {
   float *d_du = nullptr, *d_costs = nullptr;
   unsigned char *d_crash = nullptr;
   unsigned int *d_baseline = nullptr, *d_done = nullptr;
-  float *d_block_partials = nullptr, *d_shard = nullptr;
+  float *d_block_partials = nullptr, *d_group_partials = nullptr, *d_shard = nullptr;
+  int ngroups = 1;
   // single GPU, one controller, few weighting CTAs: finalize_kernel adds the per-CTA partial records up itself and the
   // weighting kernel skips its ticket / last-CTA pass; set around the launches of the plain (unsharded) pipeline only
   bool direct_combine = false;
@@ -237,7 +238,8 @@ cudaError_t launch_noise(mppi_ctx *c, bool pull_inbox = false) {
 cudaError_t launch_weighting(mppi_ctx *c) {
   WeightParams p{};
   p.costs = c->d_costs; p.V = reinterpret_cast<const float2 *>(c->d_du); p.baseline = c->d_baseline;
-  p.block_partials = c->d_block_partials; p.shard = c->d_shard; p.done_counter = c->d_done;
+  p.block_partials = c->d_block_partials; p.group_partials = c->d_group_partials; p.shard = c->d_shard; p.done_counter = c->d_done;
+  p.ngroups = c->ngroups;
   p.n_local = c->n_local; p.T = c->T; p.nblk = c->nblk; p.rows_per_blk = c->rows_per_blk; p.shard_floats = c->shard_floats;
   p.gamma = c->gamma; p.partials_only = c->direct_combine ? 1 : 0;
   p.G = c->p2p_send ? c->p2p_size : 1; p.rank = c->p2p_rank; p.B = c->B; p.seq = c->p2p_seq;
@@ -423,6 +425,7 @@ int mppi_create(const mppi_config *cfg, mppi_ctx **out) {
     if (c->B == 1 && nblk > 32 && nblk <= 128) nblk = 32;
     c->rows_per_blk = (int)((c->n_local + nblk - 1) / nblk);
     c->nblk = (c->n_local + c->rows_per_blk - 1) / c->rows_per_blk;
+    c->ngroups = (c->nblk + COMBINE_GROUP - 1) / COMBINE_GROUP;
   }
   auto fail = [&](int code) { mppi_destroy(c); return code; };
 #define CKF(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail((int)e__); } while (0)
@@ -445,7 +448,8 @@ int mppi_create(const mppi_config *cfg, mppi_ctx **out) {
   CKF(cudaMalloc(&c->d_costs, B * n * sizeof(float)));
   CKF(cudaMalloc(&c->d_crash, B * n));
   CKF(cudaMalloc(&c->d_baseline, B * sizeof(unsigned int)));
-  CKF(cudaMalloc(&c->d_done, B * sizeof(unsigned int)));
+  CKF(cudaMalloc(&c->d_done, B * (1 + c->ngroups) * sizeof(unsigned int)));
+  CKF(cudaMalloc(&c->d_group_partials, B * c->ngroups * c->shard_floats * sizeof(float)));
   CKF(cudaMalloc(&c->d_block_partials, B * c->nblk * c->shard_floats * sizeof(float)));
   CKF(cudaMalloc(&c->d_shard, B * c->shard_floats * sizeof(float)));
   CKF(cudaMalloc(&c->d_inv_step, T * sizeof(double)));
@@ -453,7 +457,7 @@ int mppi_create(const mppi_config *cfg, mppi_ctx **out) {
   CKF(cudaMalloc(&c->d_call_counter, sizeof(uint32_t)));
   CKF(cudaMemset(c->d_call_counter, 0, sizeof(uint32_t)));
   CKF(cudaMemset(c->d_baseline, 0xff, B * sizeof(unsigned int)));
-  CKF(cudaMemset(c->d_done, 0, B * sizeof(unsigned int)));
+  CKF(cudaMemset(c->d_done, 0, B * (1 + c->ngroups) * sizeof(unsigned int)));
   CKF(cudaMemset(c->d_inbox, 0, B * c->inbox_stride * sizeof(float)));
   {
     std::vector<double> inv(T);
@@ -480,7 +484,7 @@ int mppi_destroy(mppi_ctx *c) {
   cudaFree(c->d_theta_t); cudaFree(c->d_net_structure); cudaFree(c->d_inbox); cudaFree(c->d_outbox);
   cudaFreeHost(c->h_inbox); cudaFreeHost(c->h_outbox);
   cudaFree(c->d_du); cudaFree(c->d_costs); cudaFree(c->d_crash); cudaFree(c->d_baseline); cudaFree(c->d_done);
-  cudaFree(c->d_block_partials); cudaFree(c->d_shard); cudaFree(c->d_inv_step); cudaFree(c->d_flush);
+  cudaFree(c->d_block_partials); cudaFree(c->d_group_partials); cudaFree(c->d_shard); cudaFree(c->d_inv_step); cudaFree(c->d_flush);
   for (cudaEvent_t e : c->step_events) cudaEventDestroy(e);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -1126,6 +1130,37 @@ int mppi_run_resident(mppi_ctx *c, int steps, int flush_l2, float *elapsed_ms, f
   if (!flush_l2) CK(cudaEventElapsedTime(&total, c->ev0, c->ev1));
   if (elapsed_ms) *elapsed_ms = total;
   if (rollout_kernel_ms) *rollout_kernel_ms = roll;
+  return MPPI_OK;
+}
+
+int mppi_time_stages(mppi_ctx *c, int reps, float stage_ms[4]) {
+  int rc = check_ready(c);
+  if (rc) return rc;
+  if (reps < 1 || !stage_ms || !c->have_inbox || c->injected) return MPPI_ERR_INVALID_ARG;
+  CK(cudaSetDevice(c->device));
+  cudaEvent_t ev[5];
+  for (auto &e : ev) CK(cudaEventCreate(&e));
+  for (int k = 0; k < 4; k++) stage_ms[k] = 0.0f;
+  DirectCombineScope direct(c);
+  for (int r = -1; r < reps; r++) {  // r = -1: warm-up
+    CK(cudaEventRecord(ev[0], c->stream));
+    CK(launch_noise(c));  // same counters as the in-place draws: the rollout kernel below sees the same noise either way
+    CK(cudaEventRecord(ev[1], c->stream));
+    CK(launch_rollout(c));
+    CK(cudaEventRecord(ev[2], c->stream));
+    CK(launch_weighting(c));
+    CK(cudaEventRecord(ev[3], c->stream));
+    CK(launch_finalize(c, c->d_shard, 1, 1, 1));
+    CK(cudaEventRecord(ev[4], c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (r < 0) continue;
+    for (int k = 0; k < 4; k++) {
+      float ms = 0.0f;
+      CK(cudaEventElapsedTime(&ms, ev[k], ev[k + 1]));
+      stage_ms[k] += ms / reps;
+    }
+  }
+  for (auto &e : ev) cudaEventDestroy(e);
   return MPPI_OK;
 }
 

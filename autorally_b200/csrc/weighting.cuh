@@ -86,14 +86,17 @@ __global__ void __launch_bounds__(256) sample_noise_kernel(float *__restrict__ d
 // Shard partial record per controller: [0] baseline b, [1] Z = sum exp(-gamma (c - b)),
 // [2] Q = sum exp(..)^2, [3] unused, [4 .. 4+2T) W[t][j] = sum exp(..) * V[r][t][j].
 constexpr int SHARD_HDR = 4;
+constexpr int COMBINE_GROUP = 32;  // CTAs whose partial records one group combiner adds up (weight_reduce_kernel)
 
 struct WeightParams {
   const float *costs;            // [B][n_local]
   const float2 *V;               // [B][n_local][T]
   const unsigned int *baseline;  // [B]
   float *block_partials;         // [B][nblk][shard_floats]
+  float *group_partials;         // [B][ngroups][shard_floats]: the per-CTA records of COMBINE_GROUP consecutive CTAs, summed
   float *shard;                  // [B][shard_floats]
-  unsigned int *done_counter;    // [B]
+  unsigned int *done_counter;    // [B][1 + ngroups]: tickets of the group combiners, then of the CTAs of every group
+  int ngroups;
   int n_local, T, nblk, rows_per_blk, shard_floats;
   float gamma;
   int partials_only;  // 1: stop after the per-CTA partial records; finalize_kernel adds them up itself (combine_partials)
@@ -177,6 +180,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) weight_reduce_kernel(const __gr
   const int T = p.T;
   const int nrl = max(1, 256 / T);
   const float2 *V = p.V + ((size_t)b * p.n_local + r0) * T;
+  float *out = p.block_partials + ((size_t)b * p.nblk + blk) * p.shard_floats;
   for (int c0 = 0; c0 < T; c0 += 256) {  // one pass when T <= 256
     const int rl = (T <= 256) ? tid / T : 0;
     const int c = (T <= 256) ? tid - rl * T : c0 + tid;
@@ -205,7 +209,6 @@ __global__ void __launch_bounds__(256, MIN_CTAS) weight_reduce_kernel(const __gr
     }
   }
   __syncthreads();
-  float *out = p.block_partials + ((size_t)b * p.nblk + blk) * p.shard_floats;
   if (T <= 256 && tid < T) {
     float2 acc = colsum[tid];
     for (int rl = 1; rl < nrl; rl++) { acc.x += colsum[rl * T + tid].x; acc.y += colsum[rl * T + tid].y; }
@@ -217,23 +220,48 @@ __global__ void __launch_bounds__(256, MIN_CTAS) weight_reduce_kernel(const __gr
     out[0] = base; out[1] = zz; out[2] = qq; out[3] = 0.0f;
   }
   if (p.partials_only) return;
-  // ---- last CTA of this controller combines the per-CTA partials in fixed order ----
+  // ---- two-level combine in fixed order: the last CTA of every group of COMBINE_GROUP CTAs adds the group's records up, the
+  //      last of those adds the group records up.  (One last CTA walking all 1184 records of a filled GPU was a chain of 74
+  //      dependent L2 round trips per thread, ~30 us of this kernel's 178 us at 1 M rollouts.) ----
+  const int grp = blk / COMBINE_GROUP, g0 = grp * COMBINE_GROUP, gsize = min(COMBINE_GROUP, p.nblk - g0);
+  unsigned int *tickets = p.done_counter + (size_t)b * (1 + p.ngroups);
   __threadfence();
   __syncthreads();
   if (tid == 0) {
-    const unsigned int ticket = atomicAdd(p.done_counter + b, 1u);
-    is_last = (ticket == (unsigned int)p.nblk - 1);
-    if (is_last) p.done_counter[b] = 0;  // re-arm for the next launch
+    const unsigned int ticket = atomicAdd(tickets + 1 + grp, 1u);
+    is_last = (ticket == (unsigned int)gsize - 1);
+    if (is_last) tickets[1 + grp] = 0;  // re-arm for the next launch
   }
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  const float *parts = p.block_partials + (size_t)b * p.nblk * p.shard_floats;
   float *shard = p.shard + (size_t)b * p.shard_floats;
-  for (int k = tid; k < p.shard_floats; k += 256) {
-    if (k == 0) { shard[0] = base; continue; }
-    if (k == 3 || k >= SHARD_HDR + 2 * T) { shard[k] = 0.0f; continue; }
-    shard[k] = sum_partials_fixed_order(parts, p.nblk, p.shard_floats, k);
+  {
+    const float *parts = p.block_partials + ((size_t)b * p.nblk + g0) * p.shard_floats;
+    float *dst = p.ngroups == 1 ? shard : p.group_partials + ((size_t)b * p.ngroups + grp) * p.shard_floats;
+    for (int k = tid; k < p.shard_floats; k += 256) {
+      if (k == 0) { dst[0] = base; continue; }
+      if (k == 3 || k >= SHARD_HDR + 2 * T) { dst[k] = 0.0f; continue; }
+      dst[k] = sum_partials_fixed_order(parts, gsize, p.shard_floats, k);
+    }
+  }
+  if (p.ngroups > 1) {
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned int ticket = atomicAdd(tickets, 1u);
+      is_last = (ticket == (unsigned int)p.ngroups - 1);
+      if (is_last) tickets[0] = 0;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const float *parts = p.group_partials + (size_t)b * p.ngroups * p.shard_floats;
+    for (int k = tid; k < p.shard_floats; k += 256) {
+      if (k == 0) { shard[0] = base; continue; }
+      if (k == 3 || k >= SHARD_HDR + 2 * T) { shard[k] = 0.0f; continue; }
+      shard[k] = sum_partials_fixed_order(parts, p.ngroups, p.shard_floats, k);
+    }
   }
   if (p.G > 1) {
     // fused exchange: this CTA's record goes straight into every GPU's mailbox (peer stores over NVLink), then the flags

@@ -296,6 +296,18 @@ def measure_large(kind, models, costmap, cp, state, U, n_rollouts, device, fp32_
         ms_step, nb = resident_median(ctx, steps)
         rk = statistics.median(ctx.run_resident(steps, time_rollout=True)[1] / steps for _ in range(3))
         n_local = ctx.n_local
+        # the HBM-bound stages on their own (north_star: "achieved HBM GB/s for the noise and reduction stages ... against the
+        # B200 peak"): algorithmic bytes = 8 B per rollout-step written by the sampler; 8 B per rollout-step + 4 B per rollout
+        # read by the weighting kernel
+        st = ctx.time_stages(5)
+        hbm = peaks.get("hbm_gbs") or 6650.0
+        samp_gbs = 8.0 * n_local * T_STEPS / (st["sampler"] * 1e-3) / 1e9
+        wred_gbs = (8.0 * n_local * T_STEPS + 4.0 * n_local) / (st["weighting"] * 1e-3) / 1e9
+        out["stages"] = {"ms": st, "sampler": {"bound": "hbm", "achieved": samp_gbs, "peak": hbm, "unit": "GB/s", "frac": samp_gbs / hbm,
+                                               "note": "stand-alone sample_noise_kernel (the pipeline above draws its noise inside the rollout "
+                                                       "kernel when launches_per_step is 3); Philox-multiply-bound"},
+                         "weighting": {"bound": "hbm", "achieved": wred_gbs, "peak": hbm, "unit": "GB/s", "frac": wred_gbs / hbm},
+                         "peak_source": peaks["source"]}
         out.update(rollouts=n_local, steps=steps, batches=nb, ms_per_step=ms_step, rollout_kernel_ms=rk,
                    value=n_local * T_STEPS / (ms_step * 1e-3), variant=ctx.resolved_variant(),
                    launches_per_step=ctx.last_launch_count() // steps)

@@ -214,6 +214,11 @@ int mppi_run_resident_sharded(mppi_ctx *ctx, int steps, float *elapsed_ms);
  * time spent in the rollout kernel alone.  flush_l2 != 0 writes a 256 MiB scratch buffer before every
  * step, outside the timed intervals, and sums the per-step intervals instead. */
 int mppi_run_resident(mppi_ctx *ctx, int steps, int flush_l2, float *elapsed_ms, float *rollout_kernel_ms);
+/* Measurement helper: device time (ms, CUDA events, every stage serialised, mean of `reps` repetitions) of the four stages
+ * of one pipeline on the resident inputs: {stand-alone sampler kernel (replaces curandGenerateNormal, PI/mppi_controller.cu:612;
+ * timed even when the rollout kernel draws its noise in place), rollout kernel (:72-184), weighting kernel (host min /
+ * normaliser loops + normExpKernel + weightedReductionKernel, :193-267, :627-652), finalize kernel (:468-519, :663-667)}. */
+int mppi_time_stages(mppi_ctx *ctx, int reps, float stage_ms[4]);
 int mppi_get_stream(mppi_ctx *ctx, void **cuda_stream);
 int mppi_synchronize(mppi_ctx *ctx);
 /* Number of kernels the last compute call launched (bench.py's gpu_launches). */
