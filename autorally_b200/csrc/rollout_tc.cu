@@ -35,6 +35,7 @@
 // epilogues.
 #include <cuda_fp16.h>
 #include <cmath>
+#include <cstdlib>
 #include "rollout.cuh"
 #include "rollout_launch.h"
 
@@ -56,7 +57,7 @@ constexpr float TANH_SCALE = 2.88539008177792681472f;  // 2 log2(e)
 
 // Geometry of one instantiation: 6 -> HID x NHID (tanh) -> 4.  NeuralNetModel<7,2,3,6,32,32,4> is <32, 2>, the
 // wider_deeper network 6-64-64-64-64-4 the fork ships (SRC/params/models/wider_deeper_network_08_20_2020.npz) <64, 4>.
-template <int HID, int NHID, int TPC_ = 1>
+template <int HID, int NHID, int TPC_ = 1, int CS_ = 1>
 struct Geo {
   static_assert(HID == 32 || HID == 64, "hidden width 32 or 64");
   static_assert(NHID >= 2, "at least two hidden layers");
@@ -69,7 +70,13 @@ struct Geo {
   // 13.6 ms, 65536: 1.32 -> 1.06 ms).  Small problems keep one tile per CTA so that the tiles spread over more SMs (1920
   // rollouts = 15 tiles: 0.54 ms on 15 SMs, 0.73 ms on 8).
   static constexpr int TPC = TPC_;
-  static constexpr int THREADS = TILE * TPC;
+  // Column slices: threads per rollout in the tanh epilogues.  One tile on an SM (a controller-sized problem: 1920 rollouts
+  // = 15 tiles) is a latency chain in which a single warp per scheduler works through HID tanh + FP16 splits per layer; with
+  // CS slices, warp 4 s + w (the same tensor-memory lane quarter as warp w) takes the 16-column chunks c = s (mod CS) of its
+  // 32 rollouts.  Slice 0 owns the rollouts (controls, costs, kinematics, the state); the others only run epilogues.
+  static constexpr int CS = CS_;
+  static_assert(CS == 1 || (TPC == 1 && (HID / 16) % CS == 0), "column slices: one tile per CTA, chunks divide evenly");
+  static constexpr int THREADS = TILE * TPC * CS;
   // shared-memory B matrices (FP16, canonical K-major no-swizzle: 8 rows x 16 bytes core matrices)
   static constexpr int SZ_B1 = HID * 16 * 2;              // N = HID, K = 16
   static constexpr int SZ_BH = HID * HID * 2;             // N = HID, K = HID
@@ -86,7 +93,7 @@ struct Geo {
   // weights each).  No shared-memory padding: padding the allocation to fence off extra CTAs costs L1 / texture cache
   // (unified with shared memory) and was measured 8 % slower at 1 M rollouts (profiles/exp_tc_cfg_r01.txt).  The launcher
   // falls back to padding only if a build ever uses so few registers that one more CTA would fit.
-  static constexpr int MIN_CTAS = HID == 32 ? TC_MINCTAS : (TPC == 2 ? 2 : 3);
+  static constexpr int MIN_CTAS = CS > 1 ? 1 : HID == 32 ? TC_MINCTAS : (TPC == 2 ? 2 : 3);
   static constexpr int PAD_BYTES = (227 / MIN_CTAS - 2) * 1024;
   static constexpr int SMEM_BYTES = (TC_PAD && B_BYTES < PAD_BYTES) ? PAD_BYTES : B_BYTES;
   // packed transposed parameters: per layer Wt[k][j] then b[j]
@@ -125,15 +132,34 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// one lane of a converged warp (elect.sync): the form of single-thread predicate the compiler recognises -- under a plain
+// `tid == 0` it wraps every tcgen05.mma in an ELECT / BRA.U.ANY loop over the active lanes (~65 cycles per MMA issued)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// bounded: a mis-programmed MMA must end as wrong numbers (caught by the parity tests), never as a hung GPU
+// bounded: a mis-programmed MMA must end as wrong numbers (caught by the parity tests), never as a hung GPU.
+// SPIN: poll with test_wait (one tile per SM: nobody else wants the issue slots and the wake-up from a suspended try_wait is
+// part of the latency chain); otherwise try_wait with a suspend-time hint, which sleeps in hardware.
+template <bool SPIN>
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
   if (TC_EXP == 3 || TC_EXP == 4) return true;
   uint32_t done = 0;
+  if (SPIN) {
+#pragma unroll 1
+    for (int spin = 0; spin < (1 << 26); spin++) {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                   : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+      if (done) return true;
+    }
+    return false;
+  }
 #pragma unroll 1
   for (int spin = 0; spin < (1 << 18); spin++) {
     asm volatile(
@@ -246,15 +272,18 @@ __device__ __forceinline__ void put_split(unsigned char *hi_base, unsigned char 
 
 // FUSED: the noise of a timestep pair is drawn in place from the Philox stream (philox.cuh) inside the wait for the output
 // layer's MMAs instead of being read from `du` (800-byte stride, written by a separate sampler launch).
-template <int HID, int NHID, int TPC, bool FUSED>
-__global__ void __launch_bounds__(Geo<HID, NHID, TPC>::THREADS, Geo<HID, NHID, TPC>::MIN_CTAS)
+template <int HID, int NHID, int TPC, bool FUSED, int CS>
+__global__ void __launch_bounds__(Geo<HID, NHID, TPC, CS>::THREADS, Geo<HID, NHID, TPC, CS>::MIN_CTAS)
 rollout_tc_kernel(const __grid_constant__ RolloutParams p, const __grid_constant__ TcEpilogue<HID, NHID> ep) {
-  using G = Geo<HID, NHID, TPC>;
+  using G = Geo<HID, NHID, TPC, CS>;
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) unsigned long long mma_bar_sm[G::TPC];
   __shared__ uint32_t tmem_base_slot;
   // a CTA holds TPC independent tiles that share the weights in shared memory; `tid`, `warp` are relative to the tile
-  const int cta_tid = threadIdx.x, tile = cta_tid / TILE, tid = cta_tid - tile * TILE, warp = tid >> 5;
+  // with column slices the CTA is one tile and `slice` says which chunks of the epilogues this thread takes
+  const int cta_tid = threadIdx.x, grp = cta_tid / TILE, tid = cta_tid - grp * TILE, warp = tid >> 5;
+  const int tile = CS > 1 ? 0 : grp, slice = CS > 1 ? grp : 0;
+  const bool owner = (slice == 0);
   auto tile_sync = [&]() {  // barrier among the 128 threads of this tile (named barrier 1 + tile)
     if (G::TPC == 1) __syncthreads();
     else asm volatile("bar.sync %0, %1;" ::"r"(1 + tile), "n"(TILE) : "memory");
@@ -287,7 +316,7 @@ rollout_tc_kernel(const __grid_constant__ RolloutParams p, const __grid_constant
     }
   }
   const uint32_t bar = smem_u32(&mma_bar_sm[tile]);
-  if (tid == 0) {
+  if (owner && tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -315,7 +344,7 @@ rollout_tc_kernel(const __grid_constant__ RolloutParams p, const __grid_constant
   // ---- rollout bookkeeping (rollout.cuh, R = 1) ----
   const long long total = (long long)p.B * p.n_local;
   const long long g0 = ((long long)blockIdx.x * G::TPC + tile) * TILE + tid;
-  const bool valid = g0 < total;
+  const bool valid = owner && g0 < total;
   const long long gc = valid ? g0 : 0;  // idle threads shadow rollout 0 (they must take part in every barrier) and store nothing
   const int ctrl = (int)(gc / p.n_local);
   const int lr0 = (int)(gc - (long long)ctrl * p.n_local);
@@ -365,12 +394,21 @@ rollout_tc_kernel(const __grid_constant__ RolloutParams p, const __grid_constant
     control_cost = cost_control_part(p.cp, u0, u1, du0, du1, p.nu0, p.nu1);
     split2(u0, u1, ua_hi, ua_lo);
   };
-  prepare_controls(0);
+  if (owner) prepare_controls(0);
   float front = 0.0f, back = 0.0f;  // costmap texels under the state of the current step (requested one step ahead as well)
 
+#if TC_EXP == 9  // timing experiment: cycle stamps of step 50 of rollout 0, written over its row of sampled controls
+  unsigned stamps[48];
+#pragma unroll
+  for (int k = 0; k < 48; k++) stamps[k] = 0u;
+#define TC_STAMP(k) do { if (i == 50 && cta_tid == 0 && blockIdx.x == 0) stamps[k] = clock(); } while (0)
+#else
+#define TC_STAMP(k) do { } while (0)
+#endif
   for (int i = 0; i < p.T; i++) {
+    TC_STAMP(0);
     // ---- layer 1: a = [roll, u_x, u_y, yaw rate, steering, throttle, 1 (bias), 0] as [a_hi | a_lo], one K = 16 chunk ----
-    {
+    if (owner) {
       uint32_t a[8];
       split2(s[3], s[4], a[0], a[4]);
       split2(s[5], s[6], a[1], a[5]);
@@ -381,9 +419,11 @@ rollout_tc_kernel(const __grid_constant__ RolloutParams p, const __grid_constant
     }
     wait_st();
     fence_before();
+    TC_STAMP(1);
     if (TC_EXP != 4) tile_sync();
-    if (warp == 0 && TC_EXP != 3 && TC_EXP != 4) {
-      if (tid == 0) {
+    TC_STAMP(2);
+    if (owner && warp == 0 && TC_EXP != 3 && TC_EXP != 4) {
+      if (elect_one()) {
         fence_after();
         mma_ts(tmem + G::COL_D, tmem + G::COL_A, chunk_desc(sb, G::OFF_B1A, HID, 0), IDH, 0u);
         mma_ts(tmem + G::COL_D, tmem + G::COL_A, chunk_desc(sb, G::OFF_B1B, HID, 0), IDH, 1u);
@@ -393,36 +433,44 @@ rollout_tc_kernel(const __grid_constant__ RolloutParams p, const __grid_constant
     }
     // The running cost of this step (state before the dynamics, PI/mppi_controller.cu:162-165) is spread over the waits
     // for the three layers.  Here: control + speed + crash + track, in the reference's summation order (PI/costs.cu:396-409).
+    TC_STAMP(3);
     float cost_acc = 0.0f;
-    if (i > 0 && TC_EXP != 1) {
+    if (owner && i > 0 && TC_EXP != 1) {
       bool boundary;
       const float track = cost_track_part(p.cp, front, back, boundary);
       if (boundary) crash = 1;
       const float pre = cost_pre_part(p.cp, control_cost, s[4]);
       cost_acc = __fadd_rn(__fadd_rn(pre, crash > 0 ? p.cp.crash_cost_on : 0.0f), track);
     }
-    ok = mbar_wait(bar, phase) && ok;
+    TC_STAMP(4);
+    ok = ok && mbar_wait<(CS > 1)>(bar, phase);  // after one time-out nothing waits again: a broken launch ends in seconds
     phase ^= 1u;
     fence_after();
+    TC_STAMP(5);
 
     // ---- following layers: tanh epilogue -> hi / lo activations back into TMEM -> 3 MMAs per K = 16 chunk ----
 #pragma unroll
     for (int layer = 1; layer <= NHID; layer++) {  // layer = index of the layer whose MMAs are issued here (NHID = output layer)
 #pragma unroll
       for (int c = 0; c < G::NCH; c++) {
+        if (CS > 1 && (c % CS) != slice) continue;  // warp-uniform: this slice's chunks only
         float v[16];
         uint32_t h[16];
         tmem_ld16(lane_base + G::COL_D + 16 * c, v);
         wait_ld();
+        if (c == 0) TC_STAMP(6 * layer + 0);
         if (layer == 1) activate16<true>(v, nullptr, h);
         else activate16<false>(v, &ep.eb[layer - 1][16 * c], h);
+        if (c == 0) TC_STAMP(6 * layer + 1);
         tmem_st16(lane_base + G::COL_A + 16 * c, h);
       }
       wait_st();
       fence_before();
+      TC_STAMP(6 * layer + 2);
       if (TC_EXP != 4) tile_sync();
-      if (warp == 0 && TC_EXP != 3 && TC_EXP != 4) {
-        if (tid == 0) {
+      TC_STAMP(6 * layer + 3);
+      if (owner && warp == 0 && TC_EXP != 3 && TC_EXP != 4) {
+        if (elect_one()) {
           fence_after();
           const bool last = (layer == NHID);
           const int N = last ? 16 : HID;
@@ -438,20 +486,22 @@ rollout_tc_kernel(const __grid_constant__ RolloutParams p, const __grid_constant
         }
         __syncwarp();
       }
+      TC_STAMP(6 * layer + 4);
       if (layer == NHID) break;
       // second wait: the stabilizing cost (atan of the slip angle), the NaN / 1e12 clamp and the running mean (:162-165)
-      if (layer == 1 && i > 0 && TC_EXP != 1) {
+      if (owner && layer == 1 && i > 0 && TC_EXP != 1) {
         float c = __fadd_rn(cost_acc, cost_stab_part(p.cp, s[4], s[5]));
         if (c > 1e12f || isnan(c)) c = 1e12f;
         running = (float)((double)running + (double)__fsub_rn(c, running) * p.inv_step[i]);
       }
-      ok = mbar_wait(bar, phase) && ok;
+      ok = ok && mbar_wait<(CS > 1)>(bar, phase);  // after one time-out nothing waits again: a broken launch ends in seconds
       phase ^= 1u;
       fence_after();
+      TC_STAMP(6 * layer + 5);
     }
     // third wait: kinematics (PI/neural_net_model.cu:346-355, precise sinf / cosf); x, y, yaw of the next state do not
     // depend on the network, so they are advanced now and the next step's costmap texels and controls are requested
-    {
+    if (owner) {
       float sn, cs;
       if (TC_EXP == 5) __sincosf(s[2], &sn, &cs); else sincosf(s[2], &sn, &cs);
       const float d0 = fmaf(cs, s[4], -__fmul_rn(sn, s[5]));
@@ -461,20 +511,30 @@ rollout_tc_kernel(const __grid_constant__ RolloutParams p, const __grid_constant
       s[1] = fmaf(d1, p.dt, s[1]);
       s[2] = fmaf(d2, p.dt, s[2]);
     }
-    if (i + 1 < p.T) {
+    TC_STAMP(36);
+    if (owner && i + 1 < p.T) {
       if (TC_EXP != 1) track_lookups(p.cp, p.tex, s[0], s[1], s[2], front, back);
       prepare_controls(i + 1);
     }
-    ok = mbar_wait(bar, phase) && ok;
+    TC_STAMP(37);
+    ok = ok && mbar_wait<(CS > 1)>(bar, phase);  // after one time-out nothing waits again: a broken launch ends in seconds
     phase ^= 1u;
     fence_after();
-    float o[4];
-    tmem_ld4(lane_base + G::COL_D, o);
-    wait_ld();
+    TC_STAMP(38);
+    if (owner) {
+      float o[4];
+      tmem_ld4(lane_base + G::COL_D, o);
+      wait_ld();
 #pragma unroll
-    for (int k = 0; k < 4; k++) s[3 + k] = fmaf(__fadd_rn(o[k], ep.b_last[k]), p.dt, s[3 + k]);
-    if (fabsf(s[3]) >= 1.57f) crash = 1;  // getCrash, PI/costs.cu:301-305
+      for (int k = 0; k < 4; k++) s[3 + k] = fmaf(__fadd_rn(o[k], ep.b_last[k]), p.dt, s[3 + k]);
+      if (fabsf(s[3]) >= 1.57f) crash = 1;  // getCrash, PI/costs.cu:301-305
+    }
+    TC_STAMP(39);
   }
+#if TC_EXP == 9
+  if (cta_tid == 0 && blockIdx.x == 0)
+    for (int k = 0; k < 40; k++) row[k] = make_float2((float)(stamps[k] - stamps[0]), (float)k);
+#endif
 
   // ---- epilogue: costs, crash flags, min-cost baseline; release the tensor memory ----
   if (!ok) running = __int_as_float(0x7fc00000);  // the MMA never signalled: poison the result (tests catch it)
@@ -494,11 +554,11 @@ rollout_tc_kernel(const __grid_constant__ RolloutParams p, const __grid_constant
 
 }  // namespace tc
 
-template <int HID, int NHID, int TPC, bool FUSED>
+template <int HID, int NHID, int TPC, bool FUSED, int CS = 1>
 static cudaError_t launch_tc_f(const RolloutParams &p, cudaStream_t st, const float *host_theta_t, bool pdl) {
-  using G = tc::Geo<HID, NHID, TPC>;
+  using G = tc::Geo<HID, NHID, TPC, CS>;
   const long long total = (long long)p.B * p.n_local;
-  const unsigned grid = (unsigned)((total + G::THREADS - 1) / G::THREADS);
+  const unsigned grid = (unsigned)((total + tc::TILE * TPC - 1) / (tc::TILE * TPC));
   // the folded biases are b + rowsum(W) (tanh = 1 - 2r travels as r); theta_t holds Wt[k][j] per layer, then b[j]
   tc::TcEpilogue<HID, NHID> ep;
   for (int j = 0; j < HID; j++) ep.eb[0][j] = 1.0f;  // unused: the first layer's bias rides in the K padding of its MMA
@@ -521,7 +581,7 @@ static cudaError_t launch_tc_f(const RolloutParams &p, cudaStream_t st, const fl
   int &smem_bytes = smem_bytes_dev[dev & 63];
   if (smem_bytes == 0) {
     cudaFuncAttributes fa;
-    cudaError_t e = cudaFuncGetAttributes(&fa, tc::rollout_tc_kernel<HID, NHID, TPC, FUSED>);
+    cudaError_t e = cudaFuncGetAttributes(&fa, tc::rollout_tc_kernel<HID, NHID, TPC, FUSED, CS>);
     if (e != cudaSuccess) return e;
     int bytes = G::SMEM_BYTES;
     const long long tmem_ctas = 512 / (G::TMEM_COLS * G::TPC);  // CTAs per SM the tensor memory admits
@@ -529,7 +589,7 @@ static cudaError_t launch_tc_f(const RolloutParams &p, cudaStream_t st, const fl
     const bool smem_admits_more = (long long)(bytes + 2048) * (tmem_ctas + 1) <= 228 * 1024;
     if (regs_admit_more && smem_admits_more) bytes = ((228 / (int)(tmem_ctas + 1)) - 1) * 1024;  // keep TMEM the only limiter
     if (bytes > 48 * 1024) {
-      e = cudaFuncSetAttribute(tc::rollout_tc_kernel<HID, NHID, TPC, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+      e = cudaFuncSetAttribute(tc::rollout_tc_kernel<HID, NHID, TPC, FUSED, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
       if (e != cudaSuccess) return e;
     }
     smem_bytes = bytes;
@@ -540,18 +600,20 @@ static cudaError_t launch_tc_f(const RolloutParams &p, cudaStream_t st, const fl
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, tc::rollout_tc_kernel<HID, NHID, TPC, FUSED>, p, ep);
+  return cudaLaunchKernelEx(&cfg, tc::rollout_tc_kernel<HID, NHID, TPC, FUSED, CS>, p, ep);
 }
 
-template <int HID, int NHID, int TPC>
+template <int HID, int NHID, int TPC, int CS = 1>
 static cudaError_t launch_tc(const RolloutParams &p, cudaStream_t st, const float *host_theta_t, bool pdl) {
-  return p.fused_noise ? launch_tc_f<HID, NHID, TPC, true>(p, st, host_theta_t, pdl) : launch_tc_f<HID, NHID, TPC, false>(p, st, host_theta_t, pdl);
+  return p.fused_noise ? launch_tc_f<HID, NHID, TPC, true, CS>(p, st, host_theta_t, pdl) : launch_tc_f<HID, NHID, TPC, false, CS>(p, st, host_theta_t, pdl);
 }
 
 cudaError_t launch_rollout_nn32_tc(const RolloutParams &p, cudaStream_t st, const float *host_theta_t, bool pdl) { return launch_tc<32, 2, 1>(p, st, host_theta_t, pdl); }
 cudaError_t launch_rollout_nn64_tc(const RolloutParams &p, cudaStream_t st, const float *host_theta_t, bool pdl) {
   // up to two one-tile CTAs per SM: spread the tiles; beyond that, two tiles per CTA share the weights (4 tiles per SM)
   const long long tiles = ((long long)p.B * p.n_local + tc::TILE - 1) / tc::TILE;
+  // one tile per SM at most (controller-sized problems): four threads per rollout share the tanh epilogues
+  if (tiles <= 148 && !getenv("MPPI_TC_NO_SLICES")) return launch_tc<64, 4, 1, 4>(p, st, host_theta_t, pdl);
   return tiles <= 2 * 148 ? launch_tc<64, 4, 1>(p, st, host_theta_t, pdl) : launch_tc<64, 4, 2>(p, st, host_theta_t, pdl);
 }
 
