@@ -148,7 +148,12 @@ int resolve_variant(const mppi_ctx *c) {
   if (c->net_kind == 64) {
     // 6-64-64-64-64-4: the tensor-core kernel at every size (1920 x 100: 5.4 ms -> see profiles/exp_tc64_r01.txt); the
     // one-rollout-per-thread FP32 kernel stays selectable and is the fallback for out-of-range biases
-    if (v != MPPI_ROLLOUT_AUTO && v != MPPI_ROLLOUT_TENSOR) return MPPI_ROLLOUT_THREAD1;
+    // (up to one wave of the layer-pipeline kernel -- two 8-rollout CTAs per SM, 2368 rollouts -- that kernel instead,
+    // rollout_pipe64.cu: 1920 x 100 in 0.27 ms against 0.45 ms; a second wave doubles its time, profiles/exp_pipe64_r02.txt)
+    const bool pipe_ok = rollout_pipe64_fits(c->T);
+    if (v == MPPI_ROLLOUT_LAYER_PIPE && pipe_ok) return MPPI_ROLLOUT_LAYER_PIPE;
+    if (v == MPPI_ROLLOUT_AUTO && pipe_ok && total <= 148 * 2 * 8) return MPPI_ROLLOUT_LAYER_PIPE;
+    if (v != MPPI_ROLLOUT_AUTO && v != MPPI_ROLLOUT_TENSOR && v != MPPI_ROLLOUT_LAYER_PIPE) return MPPI_ROLLOUT_THREAD1;
     return (c->theta_t.size() >= 13188 && tc_biases_in_range(c->theta_t.data(), 64, 4)) ? MPPI_ROLLOUT_TENSOR : MPPI_ROLLOUT_THREAD1;
   }
   if (v == MPPI_ROLLOUT_AUTO) {
@@ -182,7 +187,8 @@ cudaError_t launch_pdl(mppi_ctx *c, K kernel, dim3 grid, int block, size_t smem,
 bool supports_fused_noise(const mppi_ctx *c) {
   const long long total = (long long)c->B * c->n_local;
   if (c->cfg.dynamics == MPPI_DYNAMICS_BF) return !rollout_bf_is_split(total);
-  return c->variant == MPPI_ROLLOUT_TENSOR || c->variant == MPPI_ROLLOUT_THREAD1 || c->variant == MPPI_ROLLOUT_GENERIC;
+  return c->variant == MPPI_ROLLOUT_TENSOR || c->variant == MPPI_ROLLOUT_THREAD1 || c->variant == MPPI_ROLLOUT_GENERIC ||
+         c->variant == MPPI_ROLLOUT_LAYER_PIPE;
 }
 bool fused_noise_now(const mppi_ctx *c) {
   if (c->injected || c->fused_mode == 0 || !supports_fused_noise(c)) return false;
@@ -213,6 +219,7 @@ cudaError_t launch_rollout(mppi_ctx *c) {
   c->launches++;
   if (c->cfg.dynamics == MPPI_DYNAMICS_BF) return launch_rollout_bf(p, c->stream, small);
   if (c->variant == MPPI_ROLLOUT_GENERIC) return launch_rollout_generic(p, c->stream, c->net_structure.data(), (int)c->net_structure.size());
+  if (c->net_kind == 64 && c->variant == MPPI_ROLLOUT_LAYER_PIPE) return launch_rollout_nn64_pipe(p, c->stream);
   if (c->net_kind == 64)
     return c->variant == MPPI_ROLLOUT_TENSOR ? launch_rollout_nn64_tc(p, c->stream, c->theta_t.data(), tc_pdl) : launch_rollout_nn64_r1(p, c->stream, small);
   switch (c->variant) {

@@ -15,6 +15,9 @@ cudaError_t launch_rollout_nn32_tc(const RolloutParams &p, cudaStream_t st, cons
 cudaError_t launch_rollout_nn64_tc(const RolloutParams &p, cudaStream_t st, const float *host_theta_t, bool pdl);  // 6-64-64-64-64-4
 bool tc_biases_in_range(const float *host_theta_t, int hid, int nhid);
 cudaError_t launch_rollout_nn64_r1(const RolloutParams &p, cudaStream_t st, bool small);
+// 6-64-64-64-64-4 at controller sizes: hidden layers in the registers of one warp each, rollouts flowing through them
+cudaError_t launch_rollout_nn64_pipe(const RolloutParams &p, cudaStream_t st);
+bool rollout_pipe64_fits(int T);
 cudaError_t launch_rollout_bf(const RolloutParams &p, cudaStream_t st, bool small);
 bool rollout_bf_is_split(long long total);
 // run-time layer pack (any NeuralNetModel<7,2,3,6,...,4> with widths <= 128): rollout_generic.cu

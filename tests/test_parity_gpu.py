@@ -139,20 +139,75 @@ def test_bf_2560x100_matches_oracle(models, costmap):
     check_pair(want, got, cost_tol=2e-4)
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 10, 12])
 def test_wider_deeper_network(models, costmap, variant):
-    """6-64-64-64-64-4 (SRC/params/models/wider_deeper_network_08_20_2020.npz): AUTO runs it on the tensor-core kernel
-    (rollout_tc_kernel<64, 4>), variant 1 on the one-rollout-per-thread FP32 kernel."""
+    """6-64-64-64-64-4 (SRC/params/models/wider_deeper_network_08_20_2020.npz): AUTO runs it on the layer-pipeline kernel
+    (rollout_pipe64.cu) up to 8192 rollouts and on the tensor-core kernel (rollout_tc_kernel<64, 4>) beyond, variant 1 on
+    the one-rollout-per-thread FP32 kernel."""
     want, got = run_pair("nn", models, costmap, 256, T=60, tag="wider_deeper", negate=False, variant=variant)
     check_pair(want, got, cost_tol=3e-4)
     cp = cost_params_for(costmap)
     with make_context("nn", models, costmap, cp, 256, tag="wider_deeper", negate_yaw_der=False, variant=variant) as ctx:
-        assert ctx.resolved_variant() == (10 if variant == 0 else 1)
+        assert ctx.resolved_variant() == (12 if variant == 0 else variant)
+    with make_context("nn", models, costmap, cp, 16384, tag="wider_deeper", negate_yaw_der=False) as ctx:
+        assert ctx.resolved_variant() == 10
 
 
-def test_wider_deeper_network_1920x100_tensor_kernel(models, costmap):
-    want, got = run_pair("nn", models, costmap, 1920, T=100, tag="wider_deeper", negate=False, speed=4.0, scenario="top")
+@pytest.mark.parametrize("variant", [10, 12])
+def test_wider_deeper_network_1920x100(models, costmap, variant):
+    want, got = run_pair("nn", models, costmap, 1920, T=100, tag="wider_deeper", negate=False, speed=4.0, scenario="top", variant=variant)
     check_pair(want, got, cost_tol=3e-4)
+
+
+@pytest.mark.parametrize("N,T", [(64, 1), (64, 2), (128, 31), (192, 32), (256, 33), (4096, 100), (64, 1000)])
+def test_layer_pipeline_kernel_ragged_sizes(models, costmap, N, T):
+    """rollout_pipe64.cu: horizons around its 32-timestep blocks, one CTA up to more than two per SM, a long horizon."""
+    want, got = run_pair("nn", models, costmap, N, T=T, seed=N + T, tag="wider_deeper", negate=False, variant=12)
+    if T < 1000:
+        check_pair(want, got, cost_tol=3e-4)
+        return
+    # 1000 recurrent steps amplify last-bit differences of the 64-wide network: bookkeeping exact, costs to 1e-3, and the
+    # controls (64 rollouts: a sharply peaked weighting) to the softmax-sensitivity bound of the true-relative measure
+    np.testing.assert_array_equal(got["V"], want["V"])
+    check_costs(got["costs"], want["costs"], T, cost_tol=1e-3, min_ok=0.95)
+    check_scalars(got, want, 1e-3)
+    assert rel_err(got["U"], want["U"]).max() < TRUE_REL_BOUND
+
+
+def test_layer_pipeline_kernel_batched_sharded_and_fused(models, costmap):
+    from autorally_b200.params import ellipse_states
+    cp = cost_params_for(costmap)
+    B, N, T = 6, 128, 100
+    states = ellipse_states(B)
+    eps = np.random.default_rng(59).standard_normal((B, N, T, 2)).astype(np.float32)
+    U = np.broadcast_to(warm_controls(T), (B, T, 2)).copy()
+    kw = dict(tag="wider_deeper", negate_yaw_der=False, variant=12)
+    with make_context("nn", models, costmap, cp, N, num_controllers=B, **kw) as ctx:
+        assert ctx.resolved_variant() == 12
+        ctx.set_noise(eps)
+        got = ctx.compute_control(states, U)
+        costs = ctx.rollout_costs()
+    o = make_oracle("nn", models, costmap, cp, tag="wider_deeper", negate_yaw_der=False)
+    for b in range(B):
+        want = o.compute_control(states[b], U[b], np.zeros(4), NU, eps[b][None], threads=8)
+        check_costs(costs[b], want["costs"], T, cost_tol=3e-4, min_ok=0.97)
+        assert rel_err(got["U"][b], want["U"]).max() < 2e-4
+    # rollout shard [64, 128) of a 128-rollout controller: global indices drive the bookkeeping
+    with make_context("nn", models, costmap, cp, N, rollout_begin=64, rollout_count=64, **kw) as ctx:
+        ctx.set_noise(eps[0, 64:])
+        ctx.shard_begin(states[0], U[0])
+        V = ctx.sampled_controls()
+    want = o.compute_control(states[0], U[0], np.zeros(4), NU, eps[0][None], threads=8)
+    np.testing.assert_array_equal(V, want["V"][64:])
+    # Philox noise drawn inside the kernel = the sampler kernel's
+    res = []
+    for fused in (0, 1):
+        with make_context("nn", models, costmap, cp, 1920, seed=77, **kw) as ctx:
+            ctx.set_fused_noise(fused)
+            r = ctx.compute_control(states[0], U[0])
+            res.append((r["U"].copy(), ctx.rollout_costs().copy(), ctx.sampled_controls().copy()))
+    for a, b in zip(res[0], res[1]):
+        np.testing.assert_array_equal(a, b)
 
 
 @pytest.mark.parametrize("N,T", [(64, 1), (64, 2), (128, 7), (256, 33), (4096, 100)])

@@ -198,8 +198,9 @@ def test_randomized_scenarios_three_way(models, costmap, seed):
 
 def test_wider_deeper_network_three_way(models, costmap):
     """The fork's 6-64-64-64-64-4 network (SRC/params/models/wider_deeper_network_08_20_2020.npz) against the reference's own
-    MPPIController<NeuralNetModel<7,2,3,6,64,64,64,64,4>, MPPICosts, 1920, 8, 16> compiled from its sources: the tensor-core
-    kernel rollout_tc_kernel<64,4> (AUTO), the one-rollout-per-thread FP32 kernel, and the CPU oracle."""
+    MPPIController<NeuralNetModel<7,2,3,6,64,64,64,64,4>, MPPICosts, 1920, 8, 16> compiled from its sources: the
+    layer-pipeline kernel (AUTO at this size), the tensor-core kernel rollout_tc_kernel<64,4>, the one-rollout-per-thread FP32
+    kernel, and the CPU oracle."""
     cp = cost_params_for(costmap)
     state, U = top_state(4.0), straight_controls(100)
     theta = models["wider_deeper_theta"]
@@ -207,12 +208,12 @@ def test_wider_deeper_network_three_way(models, costmap):
         rc.set_controls(U, HIST)
         want = rc.compute_control(state)
         want["costs"], want["V"] = rc.rollout_costs(state, U, want["eps"][0])
-    for variant in (0, 1):
+    for variant in (0, 10, 1):
         with make_context("nn", models, costmap, cp, 1920, tag="wider_deeper", negate_yaw_der=False, variant=variant) as ctx:
             ctx.set_noise(want["eps"])
             got = ctx.compute_control(state, U, HIST)
             got["costs"], got["V"] = ctx.rollout_costs(), ctx.sampled_controls()
-            assert ctx.resolved_variant() == (10 if variant == 0 else 1)
+            assert ctx.resolved_variant() == (12 if variant == 0 else variant)
         compare(got, want, 100, "cuda (variant %d) vs reference, 64-wide network" % variant, cost_tol=3e-4)
     o = make_oracle("nn", models, costmap, cp, tag="wider_deeper", negate_yaw_der=False).compute_control(state, U, HIST, NU, want["eps"], threads=8)
     compare(o, want, 100, "oracle vs reference, 64-wide network", cost_tol=3e-4)
