@@ -29,12 +29,12 @@ def main():
     for f in ("pytest_%s.log" % tag, "bench_%s_n1.json" % tag, "bench_%s_reference.json" % tag):
         if have(f):
             shutil.copy(os.path.join(OUT, f), os.path.join(PROF, f.replace("pytest_", "pytest_gpu_")))
-    for name in ("1920", "1m", "131k", "bf_1m", "ref"):
+    for name in ("1920", "1m", "131k", "bf_1m", "wd64_1920", "ref"):
         f = "launches_%s_%s.csv" % (name, tag)
         if have(f):
             shutil.copy(os.path.join(OUT, f), os.path.join(PROF, f))
     traffic = {"source": "ncu --set full --clock-control none (tools/gpu_profile_r02.sh %s); per launch, cold cache" % tag, "configs": {}}
-    for name in ("1920", "1m", "131k", "bf_1m", "bf"):
+    for name in ("1920", "1m", "131k", "bf_1m", "bf", "wd64_1920"):
         rep = os.path.join(OUT, "prof_%s_%s.ncu-rep" % (name, tag))
         if not os.path.exists(rep):
             continue
@@ -61,7 +61,7 @@ def main():
             cfg[kname] = {"dram_read_bytes": float(r[col["dram__bytes_read.sum"]]), "dram_write_bytes": float(r[col["dram__bytes_write.sum"]]),
                           "duration_us": float(r[col["gpu__time_duration.sum"]]) / 1e3}
         traffic["configs"][name] = cfg
-        kern = {"1920": "rollout_half", "1m": "rollout_tc", "131k": "rollout_tc", "bf_1m": "rollout_kernel", "bf": "rollout_bf"}[name]
+        kern = {"1920": "rollout_half", "1m": "rollout_tc", "131k": "rollout_tc", "bf_1m": "rollout_kernel", "bf": "rollout_bf", "wd64_1920": "rollout_pipe64"}[name]
         with open(os.path.join(PROF, "ncu_%s_%s_lines.txt" % (name, tag)), "w") as fh:
             subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), rep, kern, "40"], stdout=fh)
     if traffic["configs"]:

@@ -28,15 +28,18 @@ P1M="python tools/profile_step.py --rollouts 1048576 --steps 2"
 P131K="python tools/profile_step.py --rollouts 131072 --steps 3"
 PBF1M="python tools/profile_step.py --rollouts 1048576 --steps 2 --dynamics bf"
 PBF="python tools/profile_step.py --rollouts 2560 --steps 6 --dynamics bf"
+PWD64="python tools/profile_step.py --rollouts 1920 --steps 6 --tag wider_deeper"
 run_list 1920 40 $P1920
 run_list 1m 12 $P1M
 run_list 131k 12 $P131K
 run_list bf_1m 12 $PBF1M
+run_list wd64_1920 40 $PWD64
 run_list ref 80 python tools/ref_latency.py 3
 run_full 1920 "-s 8 -c 4" $P1920
 run_full 1m "-s 3 -c 3" $P1M
 run_full 131k "-k regex:rollout_tc -s 1 -c 1" $P131K
 run_full bf_1m "-k regex:rollout_kernel -s 1 -c 1" $PBF1M
 run_full bf "-k regex:rollout_bf -s 2 -c 1" $PBF
-cat $OUT/plain_1920_$TAG.log $OUT/plain_1m_$TAG.log $OUT/plain_131k_$TAG.log $OUT/plain_bf_1m_$TAG.log $OUT/plain_ref_$TAG.log
+run_full wd64_1920 "-k regex:rollout_pipe64 -s 2 -c 1" $PWD64
+cat $OUT/plain_wd64_1920_$TAG.log $OUT/plain_1920_$TAG.log $OUT/plain_1m_$TAG.log $OUT/plain_131k_$TAG.log $OUT/plain_bf_1m_$TAG.log $OUT/plain_ref_$TAG.log
 ls -la $OUT/*_$TAG.ncu-rep
