@@ -753,3 +753,26 @@ def test_long_horizon_and_weights_outside_shared_memory(models, costmap):
     assert rel_err(got["U"], want["U"]).max() < 2e-4
     # 1024 recurrent steps of a random network amplify last-bit differences: the nominal trajectory is held to 1e-3
     assert rel_err(got["state_solution"], want["state_solution"]).max() < 1e-3
+
+
+@pytest.mark.parametrize("tag,variant,N", [("wider_deeper", 12, 1920), ("wider_deeper", 11, 1920), ("wider_deeper", 10, 1920),
+                                           ("autorally_nnet", 11, 4096), ("autorally_nnet", 10, 32768)])
+def test_repeated_launches_are_bitwise_identical(models, costmap, tag, variant, N):
+    """The warp-specialised kernels (layer pipeline: a ring of warps handing activations over through shared memory behind one
+    barrier per tick; run-time layer kernel; column-sliced tensor-core epilogues) must not depend on scheduling: the same
+    inputs give the same bits on every launch."""
+    cp = cost_params_for(costmap)
+    T = 100
+    eps = np.random.default_rng(61).standard_normal((1, N, T, 2)).astype(np.float32)
+    state, U = top_state(4.0), straight_controls(T)
+    with make_context("nn", models, costmap, cp, N, tag=tag, negate_yaw_der=(tag != "wider_deeper"), variant=variant) as ctx:
+        assert ctx.resolved_variant() == variant
+        first = None
+        for _ in range(6):
+            ctx.set_noise(eps)
+            r = ctx.compute_control(state, U)
+            got = (ctx.rollout_costs().copy(), ctx.sampled_controls().copy(), r["U"].copy(), r["state_solution"].copy())
+            if first is None:
+                first = got
+            for a, b in zip(first, got):
+                np.testing.assert_array_equal(a, b)
