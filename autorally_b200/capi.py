@@ -18,7 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libmppi_b200.so")
 
 MPPI_DYNAMICS_NN, MPPI_DYNAMICS_BF = 0, 1
-ROLLOUT_AUTO, ROLLOUT_THREAD1, ROLLOUT_THREAD2, ROLLOUT_HALF16, ROLLOUT_TENSOR, ROLLOUT_GENERIC, ROLLOUT_LAYER_PIPE = 0, 1, 2, 9, 10, 11, 12
+ROLLOUT_AUTO, ROLLOUT_THREAD1, ROLLOUT_THREAD2, ROLLOUT_HALF16, ROLLOUT_TENSOR, ROLLOUT_GENERIC, ROLLOUT_LAYER_PIPE, ROLLOUT_WARP32 = 0, 1, 2, 9, 10, 11, 12, 13
 MPPI_ERR_NO_DEVICE = -4
 
 c_float_p = ctypes.POINTER(ctypes.c_float)

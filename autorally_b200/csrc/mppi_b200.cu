@@ -161,13 +161,16 @@ int resolve_variant(const mppi_ctx *c) {
     // tiles (16384 rollouts: 128 tiles, under one per SM) and grows slowly beyond it; one rollout per half-warp takes 123 us
     // at 8192 and 232 us at 16384 rollouts, 428 us at 32768 (tensor: 270 us).  The FFMA2 kernel (THREAD2) is slower than the
     // tensor-core kernel at every size (1M rollouts: 7.2 ms vs 3.5 ms) and stays as a selectable variant.
-    if (total <= 16384) v = MPPI_ROLLOUT_HALF16;
+    // up to 1024 rollouts (at most 7 warps per SM) one rollout per WARP is shorter still: 256 rollouts 32.9 vs 36.9 us
+    if (total <= 1024) v = MPPI_ROLLOUT_WARP32;
+    else if (total <= 16384) v = MPPI_ROLLOUT_HALF16;
     else v = MPPI_ROLLOUT_TENSOR;
   }
   // the tensor-core kernel folds the hidden-layer biases into its exponentials as e^(2 b1) and e^(2 (b2 + rowsum W2))
   // (rollout_tc.cu): beyond +-40 these would leave the FP32 range, so such a network runs on the FFMA2 kernel instead
   if (v == MPPI_ROLLOUT_TENSOR && !(c->theta_t.size() >= 1412 && tc_biases_in_range(c->theta_t.data(), 32, 2))) v = MPPI_ROLLOUT_THREAD2;
-  if (v != MPPI_ROLLOUT_THREAD1 && v != MPPI_ROLLOUT_THREAD2 && v != MPPI_ROLLOUT_HALF16 && v != MPPI_ROLLOUT_TENSOR) v = MPPI_ROLLOUT_THREAD1;
+  if (v != MPPI_ROLLOUT_THREAD1 && v != MPPI_ROLLOUT_THREAD2 && v != MPPI_ROLLOUT_HALF16 && v != MPPI_ROLLOUT_TENSOR && v != MPPI_ROLLOUT_WARP32)
+    v = MPPI_ROLLOUT_THREAD1;
   return v;
 }
 
@@ -226,6 +229,7 @@ cudaError_t launch_rollout(mppi_ctx *c) {
     case MPPI_ROLLOUT_THREAD2: return launch_rollout_nn32_r2(p, c->stream, small);
     case MPPI_ROLLOUT_TENSOR: return launch_rollout_nn32_tc(p, c->stream, c->theta_t.data(), tc_pdl);
     case MPPI_ROLLOUT_HALF16: return launch_rollout_nn32_half(p, c->stream, c->pdl && !c->injected);
+    case MPPI_ROLLOUT_WARP32: return launch_rollout_nn32_warp(p, c->stream, c->pdl && !c->injected);
     default: return launch_rollout_nn32_r1(p, c->stream, small);
   }
 }

@@ -10,6 +10,7 @@ cudaError_t launch_rollout_nn32_r1(const RolloutParams &p, cudaStream_t st, bool
 cudaError_t launch_rollout_nn32_r2(const RolloutParams &p, cudaStream_t st, bool small);
 // pdl: launch with programmatic stream serialization (the kernel overlaps its prologue with its predecessor's tail)
 cudaError_t launch_rollout_nn32_half(const RolloutParams &p, cudaStream_t st, bool pdl);
+cudaError_t launch_rollout_nn32_warp(const RolloutParams &p, cudaStream_t st, bool pdl);  // one rollout per warp (<= 2368 rollouts)
 // tcgen05 tensor-core MLP (FP16 hi/lo split, activations in tensor memory): the filled-GPU kernel
 cudaError_t launch_rollout_nn32_tc(const RolloutParams &p, cudaStream_t st, const float *host_theta_t, bool pdl);
 cudaError_t launch_rollout_nn64_tc(const RolloutParams &p, cudaStream_t st, const float *host_theta_t, bool pdl);  // 6-64-64-64-64-4

@@ -55,8 +55,9 @@ enum {
   MPPI_ROLLOUT_HALF16 = 9,  /* one rollout per half-warp, FFMA2 over neuron pairs, deferred running mean: the latency default */
   MPPI_ROLLOUT_TENSOR = 10, /* one rollout per thread, layer contractions on tcgen05 (FP16 hi/lo split, A in tensor memory) */
   MPPI_ROLLOUT_GENERIC = 11, /* run-time layer pack (NeuralNetModel<7,2,3,6,...,4>, widths <= 128): one or two rollouts per warp, FP32 */
-  MPPI_ROLLOUT_LAYER_PIPE = 12 /* 6-64-64-64-64-4 only: each hidden layer in the registers of one warp, rollouts flow through the warps: the
-                                  latency default of that network up to 2368 rollouts (one wave) */
+  MPPI_ROLLOUT_LAYER_PIPE = 12, /* 6-64-64-64-64-4 only: each hidden layer in the registers of one warp, rollouts flow through the warps: the
+                                   latency default of that network up to 2368 rollouts (one wave) */
+  MPPI_ROLLOUT_WARP32 = 13 /* 6-32-32-4: one rollout per warp, one neuron per lane, weights in registers: the latency default up to 1024 rollouts */
 };
 
 /* Replaces the MPPIController template/ctor arguments (PI/mppi_controller.cuh:52-53,101-102) plus the

@@ -109,7 +109,7 @@ def check_pair(want, got, cost_tol=1e-4, u_tol=1e-4):
     assert got["launches"] >= 3
 
 
-@pytest.mark.parametrize("variant", [1, 2, 9, 10])
+@pytest.mark.parametrize("variant", [1, 2, 9, 10, 13])
 @pytest.mark.parametrize("speed", [0.0, 4.0, 8.0])
 def test_nn_1920x100_matches_oracle(models, costmap, variant, speed):
     """BASELINE config 2: path_integral_nn, 1920 rollouts x 100 steps, synthetic ellipse costmap."""
@@ -117,7 +117,7 @@ def test_nn_1920x100_matches_oracle(models, costmap, variant, speed):
     check_pair(want, got)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 9, 10])
+@pytest.mark.parametrize("variant", [1, 2, 9, 10, 13])
 @pytest.mark.parametrize("gamma", [0.15, 0.01])
 def test_nn_spread_weights_match_oracle(models, costmap, variant, gamma):
     """Flat top of the ellipse at 4 m/s: ~30% of the rollouts survive and the weights are spread over many
@@ -407,6 +407,8 @@ def test_auto_picks_the_tensor_kernel_at_65536_and_matches_oracle(models, costma
         assert ctx.resolved_variant() == 10
     with make_context("nn", models, costmap, cp, 1920) as ctx:
         assert ctx.resolved_variant() == 9
+    with make_context("nn", models, costmap, cp, 1024) as ctx:
+        assert ctx.resolved_variant() == 13
 
 
 def test_1m_rollouts_tensor_and_ffma2_kernels_agree(models, costmap):
@@ -651,7 +653,7 @@ def test_bf_sharded_rollouts_reproduce_unsharded_answer(models, costmap):
         ctx.close()
 
 
-@pytest.mark.parametrize("variant", [9, 10])
+@pytest.mark.parametrize("variant", [9, 10, 13])
 def test_multiple_iterations_on_the_default_kernels(models, costmap, variant):
     """num_iters > 1 (PI/mppi_controller.cu:609) on the half-warp latency kernel and the tensor-core kernel."""
     cp = cost_params_for(costmap)
@@ -776,3 +778,44 @@ def test_repeated_launches_are_bitwise_identical(models, costmap, tag, variant, 
                 first = got
             for a, b in zip(first, got):
                 np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize("N,T", [(64, 1), (64, 2), (128, 31), (192, 32), (256, 33), (1920, 100), (4096, 70), (64, 1000)])
+def test_warp_per_rollout_kernel_ragged_sizes(models, costmap, N, T):
+    """rollout_warp32.cu (variant 13): horizons around its 32-timestep blocks, more rollouts than one wave, a long horizon."""
+    want, got = run_pair("nn", models, costmap, N, T=T, seed=N + T, variant=13)
+    if T < 1000:
+        check_pair(want, got)
+        return
+    np.testing.assert_array_equal(got["V"], want["V"])
+    check_costs(got["costs"], want["costs"], T, cost_tol=1e-3, min_ok=0.95)
+    assert rel_err(got["U"], want["U"]).max() < TRUE_REL_BOUND
+
+
+def test_warp_per_rollout_kernel_batched_sharded_and_cost_terms(models, costmap):
+    from autorally_b200.params import ellipse_states
+    cp = cost_params_for(costmap)
+    B, N, T = 6, 128, 100
+    states = ellipse_states(B)
+    eps = np.random.default_rng(67).standard_normal((B, N, T, 2)).astype(np.float32)
+    U = np.broadcast_to(warm_controls(T), (B, T, 2)).copy()
+    with make_context("nn", models, costmap, cp, N, num_controllers=B, variant=13) as ctx:
+        assert ctx.resolved_variant() == 13
+        ctx.set_noise(eps)
+        got = ctx.compute_control(states, U)
+        costs = ctx.rollout_costs()
+    o = make_oracle("nn", models, costmap, cp)
+    for b in range(B):
+        want = o.compute_control(states[b], U[b], np.zeros(4), NU, eps[b][None], threads=8)
+        check_costs(costs[b], want["costs"], T, min_ok=0.98)
+        assert rel_err(got["U"][b], want["U"]).max() < 1e-4
+    with make_context("nn", models, costmap, cp, N, rollout_begin=64, rollout_count=64, variant=13) as ctx:
+        ctx.set_noise(eps[0, 64:])
+        ctx.shard_begin(states[0], U[0])
+        V = ctx.sampled_controls()
+    want = o.compute_control(states[0], U[0], np.zeros(4), NU, eps[0][None], threads=8)
+    np.testing.assert_array_equal(V, want["V"][64:])
+    # every cost term and an optimisation delay (as test_opt_delay_and_cost_terms)
+    want, got = run_pair("nn", models, costmap, 1920, variant=13, opt_delay=3,
+                         cp_over=dict(steering_coeff=0.4, throttle_coeff=0.2, track_slop=0.05, l1_cost=True, max_slip_ang=0.4))
+    check_pair(want, got)

@@ -23,6 +23,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "gen":
     cases = [c for c in cases if c[2] == 11 and c[3] <= 16384]
 if len(sys.argv) > 1 and sys.argv[1] == "pipe":
     cases = [("wider_deeper", None, v, N) for N in (256, 1024, 1920, 4096, 8192, 16384) for v in (12, 10)]
+if len(sys.argv) > 1 and sys.argv[1] == "lat":
+    cases = [("autorally_nnet", None, v, N) for N in (256, 1024, 1920, 2368, 2432, 4096, 8192) for v in (9, 13)]
 if len(sys.argv) > 1 and sys.argv[1] == "tc32":
     cases = [("autorally_nnet", None, 10, N) for N in (1920, 16384, 32768, 131072, 1 << 20)]
 for tag, st, variant, N in cases:
