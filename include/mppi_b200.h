@@ -43,8 +43,9 @@ enum {
 
 enum { MPPI_DYNAMICS_NN = 0, MPPI_DYNAMICS_BF = 1 };
 
-/* Rollout-kernel variants (mppi_config.rollout_variant).  AUTO picks by network and problem size: 6-32-32-4 up to 16384
- * rollouts HALF16, above TENSOR; 6-64-64-64-64-4 always TENSOR; any other layer pack (widths <= 128) GENERIC; basis
+/* Rollout-kernel variants (mppi_config.rollout_variant).  AUTO picks by network and problem size (rollouts of all
+ * controllers of the context together): 6-32-32-4 up to 1024 rollouts WARP32, up to 16384 HALF16, above TENSOR;
+ * 6-64-64-64-64-4 up to 2368 rollouts LAYER_PIPE, above TENSOR; any other layer pack (widths <= 128) GENERIC; basis
  * functions THREAD1.  A network whose folded biases would leave the FP32 range in the tensor kernel's e^(2b) constants
  * (|b| >= 40) runs on the FP32 kernels instead.  The numeric values are stable (3-8 were experimental designs of round 1
  * and are retired). */
