@@ -27,6 +27,16 @@ if len(sys.argv) > 1 and sys.argv[1] == "lat":
     cases = [("autorally_nnet", None, v, N) for N in (256, 1024, 1920, 2368, 2432, 4096, 8192) for v in (9, 13)]
 if len(sys.argv) > 1 and sys.argv[1] == "tc32":
     cases = [("autorally_nnet", None, 10, N) for N in (1920, 16384, 32768, 131072, 1 << 20)]
+if len(sys.argv) > 1 and sys.argv[1] == "bf":
+    for N in (2560, 1 << 20):
+        with make_context("bf", models, costmap, cp, N) as ctx:
+            ctx.compute_control(state, U)
+            steps = 20 if N <= 16384 else 3
+            ctx.run_resident(2)
+            best = min(ctx.run_resident(steps)[0] / steps for _ in range(3))
+            ms, rk = ctx.run_resident(steps, time_rollout=True)
+            print("basis functions N=%-8d step %.4f ms  rollout kernel %.4f ms" % (N, best, rk / steps), flush=True)
+    cases = []
 for tag, st, variant, N in cases:
     kw = {}
     if st is not None:
