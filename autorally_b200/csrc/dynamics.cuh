@@ -245,11 +245,13 @@ __device__ __forceinline__ float div_refined(float x, float c, float rc) {
   const float r = fmaf(-q, c, x);
   return fmaf(r, rc, q);
 }
-#define MPPI_DIVC(x, c) div_refined((x), (c), 1.0f / (c))
+// divisor of basis function i (PI/car_bfs.cuh), folded into the staged weights
+constexpr double kBfDivisor[25] = {1.0, 10.0, 1200.0, 1440000.0, 1728000000.0, 25.0, 10.0, 10.0, 1.0, 40.0, 1400.0, 1960000.0, 2744000000.0,
+                                   40.0, 1600.0, 64000.0, 50.0, 1.0, 1.0, 3.0, 5.0, 100.0, 1000.0, 1.0, 1.0};
 
 struct CarBasisDyn {
   static constexpr int R = 1;
-  static constexpr int SMEM_FLOATS = 100;  // theta TRANSPOSED [25][4] (mppi_set_bf_params): one LDS.128 feeds the four outputs of a basis function
+  static constexpr int SMEM_FLOATS = 100;  // theta TRANSPOSED and pre-divided [25][4] (mppi_set_bf_params): one LDS.128 feeds the four outputs of a basis function
   static constexpr int THREAD_SMEM_FLOATS = 0;
   __device__ __forceinline__ static void deriv(const float *__restrict__ sw, float *, const float (&in)[6][1], float (&out)[4][1]) {
     const float roll = in[0][0], vx = in[1][0], vy = in[2][0], wz = in[3][0], steer = in[4][0], thr = in[5][0];
@@ -263,7 +265,11 @@ struct CarBasisDyn {
     // tan(atan(a) - s) = (a - tan s) / (1 + a tan s): tan(steer) depends on the control only, i.e. it is off the critical path of
     // the state recursion, and the atanf / tanf pair that sat on it (~100 instructions, ~230 cycles) becomes one refined division.
     // The two forms differ by a few float ulps (each of atanf, tanf is accurate to 2-4 ulp itself).
-    const float ts = tanf(steer);
+    // sin and tan of the steering angle from ONE sincosf (tan = sin / cos by a refined division; |steer| <= 1 after the clamp)
+    float ss, cs;
+    sincosf(steer, &ss, &cs);
+    const float c0 = rcp_approx(cs);
+    const float ts = div_refined(ss, cs, fmaf(fmaf(-cs, c0, 1.0f), c0, c0));
     float tf = -ts;
     if (moving) {
       const float den = fmaf(front_arg, ts, 1.0f);
@@ -271,31 +277,34 @@ struct CarBasisDyn {
       tf = div_refined(front_arg - ts, den, fmaf(fmaf(-den, d0, 1.0f), d0, d0));
     }
     const float rear = ratio_y - div_refined(0.35f * wz, vx, rvx);
-    const float ss = sinf(steer);
+    // The constant divisors of the basis functions (PI/car_bfs.cuh: u_x / 10, sin(d) tan(a_f) / 1200, ...) are folded into the
+    // staged weights (theta_t[i][j] = theta[j][i] / c_i, kBfDivisor, mppi_set_bf_params): phi here are the numerators, and the
+    // 22 refined divisions of a timestep (66 instructions, 15 % of the kernel) are gone.  RN(w / c) x instead of w RN(x / c):
+    // one float ulp per term.
     float phi[25];
     phi[0] = thr;
-    phi[1] = MPPI_DIVC(vx, 10.0f);
-    phi[2] = MPPI_DIVC(ss * tf, 1200.0f);
-    phi[3] = MPPI_DIVC(ss * tf * fabsf(tf), 1440000.0f);
-    phi[4] = MPPI_DIVC(ss * (tf * tf * tf), 1728000000.0f);
-    phi[5] = MPPI_DIVC(wz * vy, 25.0f);
-    phi[6] = MPPI_DIVC(wz, 10.0f);
-    phi[7] = MPPI_DIVC(vy, 10.0f);
+    phi[1] = vx;
+    phi[2] = ss * tf;
+    phi[3] = ss * tf * fabsf(tf);
+    phi[4] = ss * (tf * tf * tf);
+    phi[5] = wz * vy;
+    phi[6] = wz;
+    phi[7] = vy;
     phi[8] = ss;
-    phi[9] = moving ? MPPI_DIVC(ratio_y, 40.0f) : 0.0f;
-    phi[10] = MPPI_DIVC(tf, 1400.0f);
-    phi[11] = MPPI_DIVC(tf * fabsf(tf), 1960000.0f);
-    phi[12] = MPPI_DIVC(tf * tf * tf, 2744000000.0f);
-    phi[13] = moving ? MPPI_DIVC(rear, 40.0f) : 0.0f;
-    phi[14] = moving ? MPPI_DIVC(rear * fabsf(rear), 1600.0f) : 0.0f;
-    phi[15] = moving ? MPPI_DIVC(rear * rear * rear, 64000.0f) : 0.0f;
-    phi[16] = MPPI_DIVC(wz * vx, 50.0f);
+    phi[9] = moving ? ratio_y : 0.0f;
+    phi[10] = tf;
+    phi[11] = tf * fabsf(tf);
+    phi[12] = tf * tf * tf;
+    phi[13] = moving ? rear : 0.0f;
+    phi[14] = moving ? rear * fabsf(rear) : 0.0f;
+    phi[15] = moving ? rear * rear * rear : 0.0f;
+    phi[16] = wz * vx;
     phi[17] = roll;
     phi[18] = roll * wz;
-    phi[19] = MPPI_DIVC(roll * vx, 3.0f);
-    phi[20] = MPPI_DIVC(roll * vx * wz, 5.0f);
-    phi[21] = MPPI_DIVC(vx * vx, 100.0f);
-    phi[22] = MPPI_DIVC(vx * vx * vx, 1000.0f);
+    phi[19] = roll * vx;
+    phi[20] = roll * vx * wz;
+    phi[21] = vx * vx;
+    phi[22] = vx * vx * vx;
     phi[23] = thr * thr;
     phi[24] = thr * thr * thr;
     // theta . phi, i ascending per output (the order of PI/generalized_linear.cu:225-245 with one y-thread); the weights of

@@ -569,10 +569,11 @@ int mppi_set_nn_params(mppi_ctx *c, const float *theta, const int *net_structure
 int mppi_set_bf_params(mppi_ctx *c, const float *theta) {
   if (!c || !theta) return MPPI_ERR_INVALID_ARG;
   if (c->cfg.dynamics != MPPI_DYNAMICS_BF) return MPPI_ERR_INVALID_ARG;
-  // theta 4 x 25 row-major (PI/generalized_linear.cu:100-116) -> transposed [25][4] for the kernels (CarBasisDyn::deriv)
+  // theta 4 x 25 row-major (PI/generalized_linear.cu:100-116) -> transposed [25][4] for the kernels, each row divided by its
+  // basis function's constant divisor (CarBasisDyn::deriv evaluates the numerators only)
   c->theta_t.assign(100, 0.0f);
   for (int j = 0; j < 4; j++)
-    for (int i = 0; i < 25; i++) c->theta_t[i * 4 + j] = theta[j * 25 + i];
+    for (int i = 0; i < 25; i++) c->theta_t[i * 4 + j] = (float)((double)theta[j * 25 + i] / kBfDivisor[i]);
   c->variant = MPPI_ROLLOUT_THREAD1;
   return upload_theta(c);
 }
