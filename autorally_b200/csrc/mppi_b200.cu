@@ -59,6 +59,8 @@ struct mppi_ctx {
   std::vector<int> net_structure;
   std::vector<float> theta_t;
   float *d_theta_t = nullptr;
+  std::vector<float> theta_fold;  // 6-32-32-4: folded copy (fold_nn32), stored behind theta_t in the same device buffer
+  float *d_theta_fold = nullptr;
   int *d_net_structure = nullptr;
   size_t theta_t_capacity = 0;
   float ranges[4] = {-0.99f, 0.99f, -0.99f, 0.65f};
@@ -203,7 +205,7 @@ bool fused_noise_now(const mppi_ctx *c) {
 cudaError_t launch_rollout(mppi_ctx *c) {
   RolloutParams p{};
   p.inbox = c->d_inbox; p.du = c->d_du; p.costs = c->d_costs; p.crash = c->d_crash; p.baseline = c->d_baseline;
-  p.theta_t = c->d_theta_t; p.inv_step = c->d_inv_step; p.inbox_stride = c->inbox_stride;
+  p.theta_t = c->d_theta_t; p.theta_fold = c->d_theta_fold; p.inv_step = c->d_inv_step; p.inbox_stride = c->inbox_stride;
   p.n_local = c->n_local; p.n_global = c->cfg.num_rollouts; p.r_begin = c->r_begin; p.T = c->T; p.B = c->B;
   p.opt_delay = c->cfg.optimization_stride; p.pure_noise_from = pure_noise_threshold(c->cfg.num_rollouts);
   p.nu0 = c->nu[0]; p.nu1 = c->nu[1];
@@ -271,7 +273,7 @@ size_t finalize_smem(const mppi_ctx *c) {
 cudaError_t launch_finalize_phase(mppi_ctx *c, const float *gathered, int G, int last_iter, int feed_back, bool push_outbox, int phase) {
   FinalizeParams p{};
   if (c->direct_combine && gathered == c->d_shard) { gathered = c->d_block_partials; p.combine_partials = c->nblk; }
-  p.gathered = gathered; p.inbox = c->d_inbox; p.outbox = push_outbox ? c->h_outbox_dev : c->d_outbox; p.theta_t = c->d_theta_t;
+  p.gathered = gathered; p.inbox = c->d_inbox; p.outbox = push_outbox ? c->h_outbox_dev : c->d_outbox; p.theta_t = c->d_theta_t; p.theta_fold = c->d_theta_fold;
   p.net_structure = c->d_net_structure;
   p.num_layers = c->cfg.dynamics == MPPI_DYNAMICS_BF ? 0 : (int)c->net_structure.size();
   p.is_nn32 = (c->cfg.dynamics == MPPI_DYNAMICS_NN && c->net_kind == 32) ? 1 : 0;
@@ -508,11 +510,42 @@ int mppi_destroy(mppi_ctx *c) {
   return MPPI_OK;
 }
 
+// 6-32-32-4, packed transposed layout [W1t 6x32 | b1 | W2t 32x32 | b2 | W3t 32x4 | b3]: the weights the latency kernels and the
+// nominal trajectory use.  With s = 2 log2(e) and r = 1 / (2^x + 1), tanh(y) = 1 - 2 r(s y):
+//   layer 1: x1 = (s W1) in + s b1;  layer 2 on r1: x2 = (-2 s W2) r1 + s (b2 + rowsum W2);  output on r2: (-2 W3) r2 + (b3 + rowsum W3).
+// Computed in double, rounded once.
+static void fold_nn32(const std::vector<float> &t, std::vector<float> &f) {
+  const int kW1 = 0, kB1 = 192, kW2 = 224, kB2 = 1248, kW3 = 1280, kB3 = 1408;
+  const double s = 2.88539008177792681472;
+  f.assign(1412, 0.0f);
+  for (int i = 0; i < 192; i++) f[kW1 + i] = (float)(s * (double)t[kW1 + i]);
+  for (int j = 0; j < 32; j++) f[kB1 + j] = (float)(s * (double)t[kB1 + j]);
+  for (int j = 0; j < 32; j++) {
+    double sum = t[kB2 + j];
+    for (int k = 0; k < 32; k++) {
+      sum += (double)t[kW2 + k * 32 + j];
+      f[kW2 + k * 32 + j] = (float)(-2.0 * s * (double)t[kW2 + k * 32 + j]);
+    }
+    f[kB2 + j] = (float)(s * sum);
+  }
+  for (int o = 0; o < 4; o++) {
+    double sum = t[kB3 + o];
+    for (int k = 0; k < 32; k++) {
+      sum += (double)t[kW3 + k * 4 + o];
+      f[kW3 + k * 4 + o] = (float)(-2.0 * (double)t[kW3 + k * 4 + o]);
+    }
+    f[kB3 + o] = (float)sum;
+  }
+}
+
 static int upload_theta(mppi_ctx *c) {
   c->graph_valid = false;
   CK(cudaSetDevice(c->device));
   CK(cudaStreamSynchronize(c->stream));
-  const size_t bytes = round_up((int)c->theta_t.size(), 4) * sizeof(float);
+  const bool fold = c->cfg.dynamics == MPPI_DYNAMICS_NN && c->net_kind == 32 && c->theta_t.size() == 1412;
+  if (fold) fold_nn32(c->theta_t, c->theta_fold); else c->theta_fold.clear();
+  const size_t main_floats = round_up((int)c->theta_t.size(), 4);
+  const size_t bytes = (main_floats + round_up((int)c->theta_fold.size(), 4)) * sizeof(float);
   if (bytes > c->theta_t_capacity) {
     cudaFree(c->d_theta_t);
     c->d_theta_t = nullptr;
@@ -521,6 +554,8 @@ static int upload_theta(mppi_ctx *c) {
   }
   CK(cudaMemset(c->d_theta_t, 0, bytes));
   CK(cudaMemcpy(c->d_theta_t, c->theta_t.data(), c->theta_t.size() * sizeof(float), cudaMemcpyHostToDevice));
+  c->d_theta_fold = c->d_theta_t + main_floats;
+  if (fold) CK(cudaMemcpy(c->d_theta_fold, c->theta_fold.data(), c->theta_fold.size() * sizeof(float), cudaMemcpyHostToDevice));
   const size_t fsm = finalize_smem(c);
   if (fsm > 48 * 1024) {
     CK(cudaFuncSetAttribute(finalize_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));

@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(32, MINB) rollout_half_kernel(const __grid_con
   const float *inbox = p.inbox + (size_t)ctrl * p.inbox_stride;
 
   // ---- lane-resident weight slices: neurons (2l, 2l+1) of layers 1 and 2, output (l & 3) over k in [8q, 8q+8) ----
-  const float *th = p.theta_t;
+  const float *th = p.theta_fold;  // tanh scale and affine map folded into the weights (fold_nn32): activations travel as r
   float2 w1[6], w2[32];
 #pragma unroll
   for (int k = 0; k < 6; k++) w1[k] = *reinterpret_cast<const float2 *>(th + kW1 + k * 32 + 2 * l);
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(32, MINB) rollout_half_kernel(const __grid_con
       float2 t = __fmul2_rn(w1[0], bcast2(roll));
       t = __ffma2_rn(w1[1], bcast2(vx), t); t = __ffma2_rn(w1[2], bcast2(vy), t); t = __ffma2_rn(w1[3], bcast2(wz), t);
       t = __ffma2_rn(w1[4], bcast2(u0), t); t = __ffma2_rn(w1[5], bcast2(u1), t);
-      *reinterpret_cast<float2 *>(myx + 2 * l) = tanh_fast2(__fadd2_rn(t, b1));
+      *reinterpret_cast<float2 *>(myx + 2 * l) = recip_core2(__fadd2_rn(t, b1));
       __syncwarp();
       // layer 2: four accumulator pairs over k mod 4
       float2 a0 = make_float2(0.0f, 0.0f), a1 = a0, a2 = a0, a3 = a0;
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(32, MINB) rollout_half_kernel(const __grid_con
         a0 = __ffma2_rn(w2[4 * k4 + 0], bcast2(hv.x), a0); a1 = __ffma2_rn(w2[4 * k4 + 1], bcast2(hv.y), a1);
         a2 = __ffma2_rn(w2[4 * k4 + 2], bcast2(hv.z), a2); a3 = __ffma2_rn(w2[4 * k4 + 3], bcast2(hv.w), a3);
       }
-      const float2 g = tanh_fast2(__fadd2_rn(__fadd2_rn(__fadd2_rn(a0, a1), __fadd2_rn(a2, a3)), b2));
+      const float2 g = recip_core2(__fadd2_rn(__fadd2_rn(__fadd2_rn(a0, a1), __fadd2_rn(a2, a3)), b2));
       *reinterpret_cast<float2 *>(myx + 32 + 2 * l) = g;
       __syncwarp();
       // layer 3: output jo over this lane's quarter of k, (even, odd) k packed; xor tree over the 4 quarters

@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(32, 16) rollout_warp32_kernel(const __grid_con
   const float *inbox = p.inbox + (size_t)ctrl * p.inbox_stride;
 
   // ---- lane-resident weight slices: neuron `lane` of layers 1 and 2, output (lane & 3) over k in [4 o, 4 o + 4) ----
-  const float *th = p.theta_t;
+  const float *th = p.theta_fold;  // tanh scale and affine map folded into the weights (fold_nn32): activations travel as r
   float w1[6], w2[32], w3[4];
 #pragma unroll
   for (int k = 0; k < 6; k++) w1[k] = th[kW1 + k * 32 + lane];
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(32, 16) rollout_warp32_kernel(const __grid_con
       float ta = __fmul_rn(w1[0], roll), tb = __fmul_rn(w1[1], vx);
       ta = fmaf(w1[2], vy, ta); tb = fmaf(w1[3], wz, tb);
       ta = fmaf(w1[4], u0, ta); tb = fmaf(w1[5], u1, tb);
-      xbuf[lane] = tanh_fast(__fadd_rn(__fadd_rn(ta, tb), b1));
+      xbuf[lane] = recip_core(__fadd_rn(__fadd_rn(ta, tb), b1));
       __syncwarp();
       // layer 2: four partial sums over k mod 4
       float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(32, 16) rollout_warp32_kernel(const __grid_con
         a0 = fmaf(w2[4 * k4 + 0], hv.x, a0); a1 = fmaf(w2[4 * k4 + 1], hv.y, a1);
         a2 = fmaf(w2[4 * k4 + 2], hv.z, a2); a3 = fmaf(w2[4 * k4 + 3], hv.w, a3);
       }
-      xbuf[32 + lane] = tanh_fast(__fadd_rn(__fadd_rn(__fadd_rn(a0, a1), __fadd_rn(a2, a3)), b2));
+      xbuf[32 + lane] = recip_core(__fadd_rn(__fadd_rn(__fadd_rn(a0, a1), __fadd_rn(a2, a3)), b2));
       __syncwarp();
       // layer 3: output jo over this lane's octet of k; xor tree over the 8 octets
       const float4 gv = reinterpret_cast<const float4 *>(xbuf + 32)[oct];

@@ -17,7 +17,9 @@ struct WarpMlp32 {
   float w1[6], w2[32], w3[32];
   float b1, b2, b3;
 
-  // theta_t: [W1t 6x32 | b1 32 | W2t 32x32 | b2 32 | W3t 32x4 | b3 4] (global or shared memory); loads are coalesced
+  // theta_t: [W1t 6x32 | b1 32 | W2t 32x32 | b2 32 | W3t 32x4 | b3 4] (global or shared memory) in its FOLDED form (fold_nn32,
+  // mppi_b200.cu: tanh scale in layers 1 and 2, the map 1 - 2 r in layers 2 and 3), so the activations that cross lanes are
+  // r = 1 / (2^x + 1) and each activation is three dependent instructions; loads are coalesced
   __device__ __forceinline__ void load(const float *__restrict__ theta_t, int lane) {
 #pragma unroll
     for (int k = 0; k < 6; k++) w1[k] = theta_t[kW1 + k * 32 + lane];
@@ -40,7 +42,7 @@ struct WarpMlp32 {
     float t = w1[0] * roll;
     t = fmaf(w1[1], vx, t); t = fmaf(w1[2], vy, t); t = fmaf(w1[3], wz, t); t = fmaf(w1[4], u0, t); t = fmaf(w1[5], u1, t);
     float *h1 = xbuf + parity * 32;
-    h1[lane] = tanh_fast(t + b1);
+    h1[lane] = recip_core(t + b1);
     __syncwarp();
     // layer 2
     float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
@@ -51,7 +53,7 @@ struct WarpMlp32 {
       a2 = fmaf(w2[4 * k4 + 2], hv.z, a2); a3 = fmaf(w2[4 * k4 + 3], hv.w, a3);
     }
     float *h2 = xbuf + 64 + parity * 32;
-    h2[lane] = tanh_fast(((a0 + a1) + (a2 + a3)) + b2);
+    h2[lane] = recip_core(((a0 + a1) + (a2 + a3)) + b2);
     __syncwarp();
     // layer 3: every lane sums all 32 products of output (lane & 3); lanes 0..3 publish the four outputs
     a0 = 0.0f; a1 = 0.0f; a2 = 0.0f; a3 = 0.0f;

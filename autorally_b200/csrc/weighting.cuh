@@ -289,6 +289,7 @@ struct FinalizeParams {
   float *inbox;           // [B][inbox_stride]  (U is rewritten for the next iteration / resident step)
   float *outbox;          // [B][outbox_stride]: result[4] | U_smoothed[2T] | U_new[2T] | state_sol[7T] | ctrl_sol[2T]
   const float *theta_t;   // NN: transposed packed weights; BF: theta transposed [25][4]
+  const float *theta_fold;  // 6-32-32-4: folded weights for WarpMlp32 (see RolloutParams)
   const int *net_structure;
   int num_layers;         // NN: entries of net_structure; 0 = basis-function model
   int is_nn32;            // the 6-32-32-4 network: nominal trajectory on the WarpMlp32 fast path
@@ -557,7 +558,7 @@ __global__ void __launch_bounds__(256, NET == 0 ? 1 : 2) finalize_kernel(const _
   float *outbox = p.outbox + (size_t)b * p.outbox_stride;
   // warp 0 fetches its slices of the network while the other warps combine the shard records
   WarpMlp32 net;
-  if (NET == 32 && p.last_iter && p.phase != 1 && tid < 32) net.load(p.theta_t, tid);
+  if (NET == 32 && p.last_iter && p.phase != 1 && tid < 32) net.load(p.theta_fold, tid);
   CtaMlp<64, 4> net64;
   if (NET == 64 && p.last_iter && p.phase != 1) net64.load(p.theta_t, tid & 63, tid >> 6);
   pdl_trigger();  // the next step's first kernel may run its prologue (weights -> shared memory, tensor-memory allocation) now
