@@ -163,8 +163,8 @@ int resolve_variant(const mppi_ctx *c) {
     // tiles (16384 rollouts: 128 tiles, under one per SM) and grows slowly beyond it; one rollout per half-warp takes 123 us
     // at 8192 and 232 us at 16384 rollouts, 428 us at 32768 (tensor: 270 us).  The FFMA2 kernel (THREAD2) is slower than the
     // tensor-core kernel at every size (1M rollouts: 7.2 ms vs 3.5 ms) and stays as a selectable variant.
-    // up to 1024 rollouts (at most 7 warps per SM) one rollout per WARP is shorter still: 256 rollouts 32.9 vs 36.9 us
-    if (total <= 1024) v = MPPI_ROLLOUT_WARP32;
+    // up to 512 rollouts (at most 4 warps per SM) one rollout per WARP is shorter still: 256 rollouts 31.0 vs 34.6 us
+    if (total <= 512) v = MPPI_ROLLOUT_WARP32;
     else if (total <= 16384) v = MPPI_ROLLOUT_HALF16;
     else v = MPPI_ROLLOUT_TENSOR;
   }

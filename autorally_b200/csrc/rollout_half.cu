@@ -8,7 +8,10 @@
 //  * lane l of a half-warp owns hidden neurons 2l, 2l+1 of both hidden layers, all their weights in registers as
 //    float2 pairs, so every MLP multiply-add is a 2-wide FFMA2 with the activation broadcast from a scalar register:
 //    layer 2 is 32 FFMA2 per lane (4 accumulator pairs, 8-deep chains) instead of 64 FFMA;
-//  * layer 3 is (4 outputs) x (4 quarters of k) over the 16 lanes: 4 FFMA2 + a two-level xor tree;
+//  * layer 3 is (4 outputs) x (4 quarters of k) over the 16 lanes: 4 FFMA2, then the 16 partial sums meet in shared memory
+//    (one store, four broadcast loads, two levels of adds: a shorter chain than a two-level xor tree plus a broadcast);
+//  * the weights are the folded copy (fold_nn32, mppi_b200.cu): tanh's factor 2 log2(e) and the map 1 - 2 r live in the
+//    weights, the activations that cross lanes are r = 1 / (2^x + 1) -- three dependent instructions instead of five;
 //  * the two rollouts of a warp share every instruction (one LDS / STS / SHFL / MUFU serves both);
 //  * per block of 16 timesteps, lane l prepares timestep i0 + l in parallel (noise, perturbation, un-clamped
 //    write-back, clamp; PI/mppi_controller.cu:130-159) and evaluates its running cost afterwards in parallel
@@ -40,8 +43,9 @@ __global__ void __launch_bounds__(32, MINB) rollout_half_kernel(const __grid_con
   float *xbuf = reinterpret_cast<float *>(smem4);  // per half-warp: h1[32], h2[32]  -> 128 floats per warp
   const int lane = threadIdx.x, l = lane & 15, hw = lane >> 4, gb = lane & 16;
   float *myx = xbuf + hw * 64;
+  float *pbuf = xbuf + 128 + hw * 16;               // per half-warp: the 16 partial sums of the output layer
   const int T = p.T;
-  float *scost = xbuf + 128 + hw * T;               // [2][T] step costs for the deferred running mean
+  float *scost = xbuf + 160 + hw * T;               // [2][T] step costs for the deferred running mean
   const unsigned full = 0xffffffffu;
   const long long gro = (long long)blockIdx.x * 2 + hw;  // rollout index over B * n_local (even, so both are valid)
   const int ctrl = (int)(gro / p.n_local);
@@ -61,7 +65,7 @@ __global__ void __launch_bounds__(32, MINB) rollout_half_kernel(const __grid_con
   float2 w3[4];  // (k, k+1) pairs of this lane's quarter
 #pragma unroll
   for (int m = 0; m < 4; m++) w3[m] = make_float2(th[kW3 + (8 * q + 2 * m) * 4 + jo], th[kW3 + (8 * q + 2 * m + 1) * 4 + jo]);
-  const float b3 = th[kB3 + jo];
+  const float2 b3q = make_float2(q == 0 ? th[kB3 + jo] : 0.0f, 0.0f);  // the output bias opens the partial sum of the first quarter
 
   const float2 *Ug = reinterpret_cast<const float2 *>(inbox + INBOX_U);
   float2 *row = reinterpret_cast<float2 *>(p.du) + (size_t)gro * T;
@@ -102,35 +106,38 @@ __global__ void __launch_bounds__(32, MINB) rollout_half_kernel(const __grid_con
     for (int ii = 0; ii < nb; ii++) {
       const float u0 = __shfl_sync(full, u0m, gb | ii), u1 = __shfl_sync(full, u1m, gb | ii);
       if (l == ii) { r_yaw = yaw; r_vx = vx; r_vy = vy; }
-      // layer 1: neurons (2l, 2l+1); k ascending, bias last (the reference's order)
-      float2 t = __fmul2_rn(w1[0], bcast2(roll));
-      t = __ffma2_rn(w1[1], bcast2(vx), t); t = __ffma2_rn(w1[2], bcast2(vy), t); t = __ffma2_rn(w1[3], bcast2(wz), t);
-      t = __ffma2_rn(w1[4], bcast2(u0), t); t = __ffma2_rn(w1[5], bcast2(u1), t);
-      *reinterpret_cast<float2 *>(myx + 2 * l) = recip_core2(__fadd2_rn(t, b1));
+      // layer 1: neurons (2l, 2l+1); two interleaved partial sums (the bias opens one of them), the controls -- which arrive
+      // through shuffles -- last
+      float2 t = __ffma2_rn(w1[0], bcast2(roll), b1), tb = __fmul2_rn(w1[1], bcast2(vx));
+      t = __ffma2_rn(w1[2], bcast2(vy), t); tb = __ffma2_rn(w1[3], bcast2(wz), tb);
+      t = __ffma2_rn(w1[4], bcast2(u0), t); tb = __ffma2_rn(w1[5], bcast2(u1), tb);
+      *reinterpret_cast<float2 *>(myx + 2 * l) = recip_core2(__fadd2_rn(t, tb));
       __syncwarp();
       // layer 2: four accumulator pairs over k mod 4
-      float2 a0 = make_float2(0.0f, 0.0f), a1 = a0, a2 = a0, a3 = a0;
+      float2 a0 = b2, a1 = make_float2(0.0f, 0.0f), a2 = a1, a3 = a1;  // the bias opens the first partial sum
 #pragma unroll
       for (int k4 = 0; k4 < 8; k4++) {
         const float4 hv = reinterpret_cast<const float4 *>(myx)[k4];
         a0 = __ffma2_rn(w2[4 * k4 + 0], bcast2(hv.x), a0); a1 = __ffma2_rn(w2[4 * k4 + 1], bcast2(hv.y), a1);
         a2 = __ffma2_rn(w2[4 * k4 + 2], bcast2(hv.z), a2); a3 = __ffma2_rn(w2[4 * k4 + 3], bcast2(hv.w), a3);
       }
-      const float2 g = recip_core2(__fadd2_rn(__fadd2_rn(__fadd2_rn(a0, a1), __fadd2_rn(a2, a3)), b2));
+      const float2 g = recip_core2(__fadd2_rn(__fadd2_rn(a0, a1), __fadd2_rn(a2, a3)));
       *reinterpret_cast<float2 *>(myx + 32 + 2 * l) = g;
       __syncwarp();
       // layer 3: output jo over this lane's quarter of k, (even, odd) k packed; xor tree over the 4 quarters
       const float4 g0 = reinterpret_cast<const float4 *>(myx + 32 + 8 * q)[0], g1 = reinterpret_cast<const float4 *>(myx + 32 + 8 * q)[1];
-      float2 s2 = __fmul2_rn(w3[0], make_float2(g0.x, g0.y));
-      s2 = __ffma2_rn(w3[1], make_float2(g0.z, g0.w), s2);
+      float2 s2 = __ffma2_rn(w3[0], make_float2(g0.x, g0.y), b3q), s3 = __fmul2_rn(w3[1], make_float2(g0.z, g0.w));
       s2 = __ffma2_rn(w3[2], make_float2(g1.x, g1.y), s2);
-      s2 = __ffma2_rn(w3[3], make_float2(g1.z, g1.w), s2);
-      float part = s2.x + s2.y;
-      part += __shfl_xor_sync(full, part, 4);
-      part += __shfl_xor_sync(full, part, 8);
-      part += b3;
-      const float o0 = __shfl_sync(full, part, gb | 0), o1 = __shfl_sync(full, part, gb | 1);
-      const float o2 = __shfl_sync(full, part, gb | 2), o3 = __shfl_sync(full, part, gb | 3);
+      s3 = __ffma2_rn(w3[3], make_float2(g1.z, g1.w), s3);
+      s2 = __fadd2_rn(s2, s3);
+      // the 16 partial sums (4 outputs x 4 quarters of k) meet in shared memory: one store, four broadcast loads and two levels of
+      // adds instead of a two-level xor tree plus a broadcast (three dependent shuffles)
+      pbuf[l] = s2.x + s2.y;  // pbuf[4 q + jo]
+      __syncwarp();
+      const float4 q0 = reinterpret_cast<const float4 *>(pbuf)[0], q1 = reinterpret_cast<const float4 *>(pbuf)[1];
+      const float4 q2 = reinterpret_cast<const float4 *>(pbuf)[2], q3 = reinterpret_cast<const float4 *>(pbuf)[3];
+      const float o0 = (q0.x + q1.x) + (q2.x + q3.x), o1 = (q0.y + q1.y) + (q2.y + q3.y);
+      const float o2 = (q0.z + q1.z) + (q2.z + q3.z), o3 = (q0.w + q1.w) + (q2.w + q3.w);
       // incrementState, PI/neural_net_model.cu:334-344 (kinematics of x, y are deferred to phase B)
       yaw = fmaf(p.negate_yaw ? -wz : wz, p.dt, yaw);
       roll = fmaf(o0, p.dt, roll); vx = fmaf(o1, p.dt, vx); vy = fmaf(o2, p.dt, vy); wz = fmaf(o3, p.dt, wz);
@@ -187,7 +194,7 @@ __global__ void __launch_bounds__(32, MINB) rollout_half_kernel(const __grid_con
 
 cudaError_t launch_rollout_nn32_half(const RolloutParams &p, cudaStream_t st, bool pdl) {
   const long long total = (long long)p.B * p.n_local;  // multiple of 64
-  const size_t smem = (128 + 2 * (size_t)p.T) * sizeof(float);
+  const size_t smem = (160 + 2 * (size_t)p.T) * sizeof(float);
   const bool roomy = total / 2 <= 148LL * 12;  // every CTA resident at once with the 166-register build
   if (smem > 48 * 1024) {
     cudaError_t e = roomy ? cudaFuncSetAttribute(rollout_half_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)

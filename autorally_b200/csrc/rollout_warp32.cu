@@ -1,4 +1,4 @@
-// rollout_warp32.cu -- the latency kernel for NeuralNetModel<7,2,3,6,32,32,4> at SMALL rollout counts (AUTO: up to 1024):
+// rollout_warp32.cu -- the latency kernel for NeuralNetModel<7,2,3,6,32,32,4> at SMALL rollout counts (AUTO: up to 512):
 // ONE ROLLOUT PER WARP, one warp per CTA.
 //
 // Replaces rolloutKernel (PI/mppi_controller.cu:72-184) + computeDynamics (PI/neural_net_model.cu:357-410), like
@@ -16,10 +16,10 @@
 //  * the step costs go to shared memory and their mean (PI/mppi_controller.cu:162-165) is taken once at the end, in
 //    double, by the 32 lanes in parallel (see rollout_half.cu).
 //
-// Measured (rollout kernel, 100 timesteps; profiles/exp_pipe64_r02.txt section 4): 256 rollouts 32.9 us (half-warp kernel
-// 36.9), 1024: 36.9 (37.8), 1920: 46.9 (43.0), 4096: 81 (64).  It loses once the SMs fill up because every activation is
-// delivered to 32 lanes instead of 16: the eight broadcast float4 loads of layer 2 alone are 32 cycles of the SM's
-// 128 B / cycle shared-memory pipe per rollout and timestep (the half-warp kernel: 16), 13 warps per SM at 1920 rollouts.
+// Measured (rollout kernel, 100 timesteps; profiles/exp_pipe64_r02.txt section 4): 256 rollouts 31.0 us (half-warp kernel
+// 34.6), 512: 32.3 (34.7), 1024: 34.8 (34.9), 1920: 44.9 (40.3), 4096: 80 (63).  It loses once the SMs fill up because every
+// activation is delivered to 32 lanes instead of 16: the eight broadcast float4 loads of layer 2 alone are 32 cycles of the
+// SM's 128 B / cycle shared-memory pipe per rollout and timestep (the half-warp kernel: 16), 13 warps per SM at 1920 rollouts.
 #include "rollout.cuh"
 #include "rollout_launch.h"
 
@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(32, 16) rollout_warp32_kernel(const __grid_con
   const int jo = lane & 3, oct = lane >> 2;
 #pragma unroll
   for (int m = 0; m < 4; m++) w3[m] = th[kW3 + (4 * oct + m) * 4 + jo];
-  const float b3 = th[kB3 + jo];
+  const float b3o = oct == 0 ? th[kB3 + jo] : 0.0f;  // the output bias opens the partial sum of the first octet
 
   const float2 *Ug = reinterpret_cast<const float2 *>(inbox + INBOX_U);
   float2 *row = reinterpret_cast<float2 *>(p.du) + (size_t)gro * T;
@@ -93,28 +93,27 @@ __global__ void __launch_bounds__(32, 16) rollout_warp32_kernel(const __grid_con
       const float u0 = __shfl_sync(full, u0m, ii), u1 = __shfl_sync(full, u1m, ii);
       if (lane == ii) { r_yaw = yaw; r_vx = vx; r_vy = vy; }
       // layer 1: neuron `lane`; two interleaved partial sums, bias last
-      float ta = __fmul_rn(w1[0], roll), tb = __fmul_rn(w1[1], vx);
+      float ta = fmaf(w1[0], roll, b1), tb = __fmul_rn(w1[1], vx);  // the bias opens one of the partial sums
       ta = fmaf(w1[2], vy, ta); tb = fmaf(w1[3], wz, tb);
       ta = fmaf(w1[4], u0, ta); tb = fmaf(w1[5], u1, tb);
-      xbuf[lane] = recip_core(__fadd_rn(__fadd_rn(ta, tb), b1));
+      xbuf[lane] = recip_core(__fadd_rn(ta, tb));
       __syncwarp();
       // layer 2: four partial sums over k mod 4
-      float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+      float a0 = b2, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
 #pragma unroll
       for (int k4 = 0; k4 < 8; k4++) {
         const float4 hv = reinterpret_cast<const float4 *>(xbuf)[k4];
         a0 = fmaf(w2[4 * k4 + 0], hv.x, a0); a1 = fmaf(w2[4 * k4 + 1], hv.y, a1);
         a2 = fmaf(w2[4 * k4 + 2], hv.z, a2); a3 = fmaf(w2[4 * k4 + 3], hv.w, a3);
       }
-      xbuf[32 + lane] = recip_core(__fadd_rn(__fadd_rn(__fadd_rn(a0, a1), __fadd_rn(a2, a3)), b2));
+      xbuf[32 + lane] = recip_core(__fadd_rn(__fadd_rn(a0, a1), __fadd_rn(a2, a3)));
       __syncwarp();
       // layer 3: output jo over this lane's octet of k; xor tree over the 8 octets
       const float4 gv = reinterpret_cast<const float4 *>(xbuf + 32)[oct];
-      float part = __fadd_rn(fmaf(w3[2], gv.z, __fmul_rn(w3[0], gv.x)), fmaf(w3[3], gv.w, __fmul_rn(w3[1], gv.y)));
+      float part = __fadd_rn(fmaf(w3[2], gv.z, fmaf(w3[0], gv.x, b3o)), fmaf(w3[3], gv.w, __fmul_rn(w3[1], gv.y)));
       part = __fadd_rn(part, __shfl_xor_sync(full, part, 4));
       part = __fadd_rn(part, __shfl_xor_sync(full, part, 8));
       part = __fadd_rn(part, __shfl_xor_sync(full, part, 16));
-      part = __fadd_rn(part, b3);
       const float o0 = __shfl_sync(full, part, 0), o1 = __shfl_sync(full, part, 1);
       const float o2 = __shfl_sync(full, part, 2), o3 = __shfl_sync(full, part, 3);
       // incrementState, PI/neural_net_model.cu:334-344 (kinematics of x, y are deferred to phase B)

@@ -44,7 +44,7 @@ enum {
 enum { MPPI_DYNAMICS_NN = 0, MPPI_DYNAMICS_BF = 1 };
 
 /* Rollout-kernel variants (mppi_config.rollout_variant).  AUTO picks by network and problem size (rollouts of all
- * controllers of the context together): 6-32-32-4 up to 1024 rollouts WARP32, up to 16384 HALF16, above TENSOR;
+ * controllers of the context together): 6-32-32-4 up to 512 rollouts WARP32, up to 16384 HALF16, above TENSOR;
  * 6-64-64-64-64-4 up to 2368 rollouts LAYER_PIPE, above TENSOR; any other layer pack (widths <= 128) GENERIC; basis
  * functions THREAD1.  A network whose folded biases would leave the FP32 range in the tensor kernel's e^(2b) constants
  * (|b| >= 40) runs on the FP32 kernels instead.  The numeric values are stable (3-8 were experimental designs of round 1
@@ -58,7 +58,7 @@ enum {
   MPPI_ROLLOUT_GENERIC = 11, /* run-time layer pack (NeuralNetModel<7,2,3,6,...,4>, widths <= 128): one or two rollouts per warp, FP32 */
   MPPI_ROLLOUT_LAYER_PIPE = 12, /* 6-64-64-64-64-4 only: each hidden layer in the registers of one warp, rollouts flow through the warps: the
                                    latency default of that network up to 2368 rollouts (one wave) */
-  MPPI_ROLLOUT_WARP32 = 13 /* 6-32-32-4: one rollout per warp, one neuron per lane, weights in registers: the latency default up to 1024 rollouts */
+  MPPI_ROLLOUT_WARP32 = 13 /* 6-32-32-4: one rollout per warp, one neuron per lane, weights in registers: the latency default up to 512 rollouts */
 };
 
 /* Replaces the MPPIController template/ctor arguments (PI/mppi_controller.cuh:52-53,101-102) plus the

@@ -407,8 +407,10 @@ def test_auto_picks_the_tensor_kernel_at_65536_and_matches_oracle(models, costma
         assert ctx.resolved_variant() == 10
     with make_context("nn", models, costmap, cp, 1920) as ctx:
         assert ctx.resolved_variant() == 9
-    with make_context("nn", models, costmap, cp, 1024) as ctx:
+    with make_context("nn", models, costmap, cp, 512) as ctx:
         assert ctx.resolved_variant() == 13
+    with make_context("nn", models, costmap, cp, 1024) as ctx:
+        assert ctx.resolved_variant() == 9
 
 
 def test_1m_rollouts_tensor_and_ffma2_kernels_agree(models, costmap):

@@ -24,7 +24,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "gen":
 if len(sys.argv) > 1 and sys.argv[1] == "pipe":
     cases = [("wider_deeper", None, v, N) for N in (256, 1024, 1920, 4096, 8192, 16384) for v in (12, 10)]
 if len(sys.argv) > 1 and sys.argv[1] == "lat":
-    cases = [("autorally_nnet", None, v, N) for N in (256, 1024, 1920, 2368, 2432, 4096, 8192) for v in (9, 13)]
+    cases = [("autorally_nnet", None, v, N) for N in (256, 512, 768, 1024, 1920, 2368, 2432, 4096, 8192) for v in (9, 13)]
 if len(sys.argv) > 1 and sys.argv[1] == "tc32":
     cases = [("autorally_nnet", None, 10, N) for N in (1920, 16384, 32768, 131072, 1 << 20)]
 if len(sys.argv) > 1 and sys.argv[1] == "bf":
