@@ -103,8 +103,11 @@ __global__ void __launch_bounds__(32, MINB) rollout_half_kernel(const __grid_con
     // ---- phase A: the serial recursion ----
     float r_yaw = 0.0f, r_vx = 0.0f, r_vy = 0.0f;
     bool r_roll = false;
+    // the controls of a timestep are fetched (shuffles) one timestep ahead: they do not depend on the state
+    float u0n = __shfl_sync(full, u0m, gb), u1n = __shfl_sync(full, u1m, gb);
     for (int ii = 0; ii < nb; ii++) {
-      const float u0 = __shfl_sync(full, u0m, gb | ii), u1 = __shfl_sync(full, u1m, gb | ii);
+      const float u0 = u0n, u1 = u1n;
+      u0n = __shfl_sync(full, u0m, gb | ((ii + 1) & 15)); u1n = __shfl_sync(full, u1m, gb | ((ii + 1) & 15));
       if (l == ii) { r_yaw = yaw; r_vx = vx; r_vy = vy; }
       // layer 1: neurons (2l, 2l+1); two interleaved partial sums (the bias opens one of them), the controls -- which arrive
       // through shuffles -- last
