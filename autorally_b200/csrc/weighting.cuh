@@ -344,8 +344,11 @@ __device__ __forceinline__ void nominal_traj_nn32(const WarpMlp32 &net, const fl
       csol[2 * (i0 + lane)] = u0m; csol[2 * (i0 + lane) + 1] = u1m;
     }
     float r_yaw = 0.0f, r_roll = 0.0f, r_vx = 0.0f, r_vy = 0.0f, r_wz = 0.0f;
+    // the controls of a timestep are fetched (shuffles) one timestep ahead: they do not depend on the state
+    float u0n = __shfl_sync(full, u0m, 0), u1n = __shfl_sync(full, u1m, 0);
     for (int ii = 0; ii < nb; ii++) {
-      const float u0 = __shfl_sync(full, u0m, ii), u1 = __shfl_sync(full, u1m, ii);
+      const float u0 = u0n, u1 = u1n;
+      u0n = __shfl_sync(full, u0m, (ii + 1) & 31); u1n = __shfl_sync(full, u1m, (ii + 1) & 31);
       if (lane == ii) { r_yaw = yaw; r_roll = roll; r_vx = vx; r_vy = vy; r_wz = wz; }
       float o0, o1, o2, o3;
       net.forward(roll, vx, vy, wz, u0, u1, act, ii & 1, lane, o0, o1, o2, o3);
