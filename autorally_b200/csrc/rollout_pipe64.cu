@@ -47,8 +47,7 @@ struct PipeGeo {
   // shared memory (floats)
   static constexpr int HB = PW;                                   // one activation vector
   static constexpr int OFF_H = 0;                                 // [stage NHID][pair NP][2][HB]
-  static constexpr int OFF_ST = OFF_H + NHID * NP * 2 * HB;       // [pair][2][8]: roll, u_x, u_y, yaw rate, yaw, x, y, crashed
-  static constexpr int OFF_CTL = OFF_ST + NP * 2 * 8;             // [pair][2][32][4]: clamped controls, perturbation
+  static constexpr int OFF_CTL = OFF_H + NHID * NP * 2 * HB;      // [pair][2][32][4]: clamped controls, perturbation
   static constexpr int OFF_REC = OFF_CTL + NP * 2 * 32 * 4;       // [pair][2][32][4]: yaw, u_x, u_y before the step; rolled-over flag after it
   static constexpr int OFF_COST = OFF_REC + NP * 2 * 32 * 4;      // [pair][2][Tpad]
 };
